@@ -1,0 +1,161 @@
+/*
+ * tfhe_b200.h -- C ABI of the B200-native TFHE bootstrapping engine.
+ *
+ * This is the drop-in boundary for rs-tfhe's hot path (gate prep -> blind
+ * rotation -> sample extract -> key switch, and its LUT variant).  Each entry
+ * point names the reference interface it replaces (file:line under the
+ * rs-tfhe tree).  Style follows the reference's only FFI precedent,
+ * src/fft/spqlios/spqlios-wrapper.cpp:10-41: an opaque handle, raw pointers,
+ * caller-allocated outputs, no exceptions/panics across the boundary.
+ *
+ * Conventions
+ *  - every function returns TFHE_OK (0) or a negative tfhe_status; the text of
+ *    the last failure on the calling thread is available from tfhe_last_error();
+ *  - host pointers are borrowed for the duration of the call only;
+ *  - ciphertexts use the reference's memory images verbatim:
+ *      TLWELv0  = u32[n+1]            (src/tlwe.rs:12-14; b is the last word)
+ *      TRLWELv1 = u32[2][N] (a then b) (src/trlwe.rs:11-14)
+ *      &[(Ciphertext, Ciphertext)] = u32[count][2][n+1] (src/gates.rs:352)
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point
+ *    fails with TFHE_ERR_CUDA.
+ *  - calls on one engine are serialised on its stream; an engine may be shared
+ *    between host threads (the Rust wrapper is Send + Sync, bootstrap/mod.rs:23).
+ */
+#ifndef TFHE_B200_H
+#define TFHE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TFHE_B200_ABI_VERSION 1
+#define TFHE_N 1024 /* params::trgsw_lv1::N -- fixed in the reference (params.rs:391) */
+
+typedef enum {
+  TFHE_OK = 0,
+  TFHE_ERR_INVALID = -1,   /* bad argument / unsupported parameter set */
+  TFHE_ERR_CUDA = -2,      /* CUDA runtime failure or no device */
+  TFHE_ERR_NO_KEY = -3,    /* cloud key not loaded */
+  TFHE_ERR_ALLOC = -4
+} tfhe_status;
+
+/* Runtime image of SecurityParams (src/params.rs:53-84); the reference fixes
+ * these at compile time to the 128-bit set (params.rs:426-469). */
+typedef struct {
+  uint32_t n;       /* tlwe_lv0::N                */
+  uint32_t N;       /* trgsw_lv1::N, must be 1024 */
+  uint32_t l;       /* trgsw_lv1::L      (1..3)   */
+  uint32_t bgbit;   /* trgsw_lv1::BGBIT           */
+  uint32_t basebit; /* trgsw_lv1::BASEBIT         */
+  uint32_t iks_t;   /* trgsw_lv1::IKS_T           */
+} tfhe_params;
+
+/* Gate selector; values are shared with the oracle.  Each is the linear
+ * pre-combination of src/gates.rs:54-150 followed by a bootstrap. */
+typedef enum {
+  TFHE_GATE_NAND = 0,  /* gates.rs:54  */
+  TFHE_GATE_AND = 1,   /* gates.rs:70  */
+  TFHE_GATE_OR = 2,    /* gates.rs:62  */
+  TFHE_GATE_XOR = 3,   /* gates.rs:78  */
+  TFHE_GATE_XNOR = 4,  /* gates.rs:86  */
+  TFHE_GATE_NOR = 5,   /* gates.rs:94  */
+  TFHE_GATE_ANDNY = 6, /* gates.rs:102 */
+  TFHE_GATE_ANDYN = 7, /* gates.rs:115 */
+  TFHE_GATE_ORNY = 8,  /* gates.rs:128 */
+  TFHE_GATE_ORYN = 9,  /* gates.rs:141 */
+  TFHE_GATE_COUNT = 10
+} tfhe_gate;
+
+typedef struct tfhe_engine tfhe_engine; /* opaque; one per (process, GPU) */
+
+/* ---- library ------------------------------------------------------------ */
+int tfhe_abi_version(void);
+const char *tfhe_last_error(void);
+/* number of CUDA devices visible (0 => every compute call will fail) */
+int tfhe_device_count(void);
+
+/* ---- engine lifetime ---------------------------------------------------- */
+/* Replaces: bootstrap::default_bootstrap() / VanillaBootstrap::new()
+ * (bootstrap/mod.rs:41-43, vanilla.rs:28-31) -- the strategy object a Gates
+ * instance owns (gates.rs:30-45).  device_id is the CUDA ordinal. */
+int tfhe_engine_create(const tfhe_params *params, int device_id, tfhe_engine **out);
+void tfhe_engine_destroy(tfhe_engine *e);
+/* Run all engine work on `cuda_stream` (a cudaStream_t; NULL restores the
+ * engine's own stream).  Lets a host runtime order engine calls with its own. */
+int tfhe_engine_set_stream(tfhe_engine *e, void *cuda_stream);
+/* Number of this library's kernels launched by the engine so far. */
+uint64_t tfhe_engine_kernel_launches(const tfhe_engine *e);
+/* Device time (ms) of the most recent call's kernels: [0]=blind rotation,
+ * [1]=key switch, measured with CUDA events on the engine stream. */
+int tfhe_engine_last_kernel_ms(tfhe_engine *e, float out_ms[2]);
+
+/* ---- cloud key ----------------------------------------------------------- */
+/* Replaces: the CloudKey a caller passes to every gate (key.rs:51-56).  Takes
+ * the reference's memory images and re-lays them out on the device once:
+ *   decomposition_offset  key.rs:52 (used verbatim)
+ *   testvec_a/b  u32[N]   key.rs:53, 91-100
+ *   ksk  u32[N][t][2^basebit][n+1]            key.rs:54, 102-122 (index :115)
+ *   bsk  f64[n][2l][2][N], each N = re[0..512) | im[0..512), values = 2*FFT
+ *        (the TRGSWLv1FFT image, trgsw.rs:52-68; klemsa.rs:110-114) */
+int tfhe_engine_load_cloud_key(tfhe_engine *e, uint32_t decomposition_offset,
+                               const uint32_t *testvec_a, const uint32_t *testvec_b,
+                               const uint32_t *ksk, const double *bsk);
+/* Multi-GPU: the device-resident, re-laid-out key is one contiguous blob.  Rank
+ * 0 loads it with tfhe_engine_load_cloud_key; the other ranks call
+ * tfhe_engine_alloc_cloud_key, receive the blob (e.g. ncclBroadcast over
+ * NVLink into tfhe_engine_cloud_key_blob's pointer) and then
+ * tfhe_engine_commit_cloud_key.  No reference counterpart (single process). */
+int tfhe_engine_alloc_cloud_key(tfhe_engine *e);
+int tfhe_engine_cloud_key_blob(tfhe_engine *e, void **device_ptr, size_t *bytes);
+int tfhe_engine_commit_cloud_key(tfhe_engine *e, uint32_t decomposition_offset);
+
+/* ---- the hot path, host buffers (H2D + kernels + D2H inside the call) ---- */
+/* Replaces: gates::batch_{nand,and,or,xor,nor,xnor}[_with_railgun]
+ * (gates.rs:352-547) and, with count==1, Gates::{nand,...,or_yn} (gates.rs:54-150). */
+int tfhe_batch_gate(tfhe_engine *e, tfhe_gate op, const uint32_t *in_pairs /*[count][2][n+1]*/,
+                    uint32_t *out /*[count][n+1]*/, size_t count);
+/* Same with a per-element gate (config "random boolean circuit batch"). */
+int tfhe_batch_gate_mixed(tfhe_engine *e, const uint8_t *ops /*[count]*/,
+                          const uint32_t *in_pairs, uint32_t *out, size_t count);
+/* Replaces: Bootstrap::bootstrap (key_switch=1, vanilla.rs:40-52) and
+ * Bootstrap::bootstrap_without_key_switch (key_switch=0, vanilla.rs:54-63,
+ * i.e. sample_extract_index_2, trlwe.rs:122-136) over a batch. */
+int tfhe_batch_bootstrap(tfhe_engine *e, const uint32_t *in /*[count][n+1]*/,
+                         uint32_t *out /*[count][n+1]*/, size_t count, int key_switch);
+/* Replaces: trgsw::batch_blind_rotate[_with_railgun] (trgsw.rs:289-305). */
+int tfhe_batch_blind_rotate(tfhe_engine *e, const uint32_t *in /*[count][n+1]*/,
+                            uint32_t *out_trlwe /*[count][2][N]*/, size_t count);
+/* Replaces: Generator::generate_lookup_table (lut/generator.rs:66-137) with the
+ * closure tabulated by the caller: f_table[x] = f(x), x < modulus.  scale <= 0
+ * selects Encoder::new's 1/(2*modulus) (lut/encoder.rs:29-42).  The table is
+ * generated on the device and kept there under *lut_id_out; lut_b_out (may be
+ * NULL) receives LookupTable.poly.b (poly.a is identically 0). */
+int tfhe_lut_generate(tfhe_engine *e, const uint32_t *f_table, uint32_t modulus, double scale,
+                      uint32_t *lut_b_out /*[N] or NULL*/, int *lut_id_out);
+/* Register a caller-made test vector (LookupTable::from_poly, lookup_table.rs:33). */
+int tfhe_lut_register(tfhe_engine *e, const uint32_t *poly_a /*[N] or NULL => 0*/,
+                      const uint32_t *poly_b /*[N]*/, int *lut_id_out);
+/* Replaces: LutBootstrap::bootstrap_lut (bootstrap/lut.rs:79-99) over a batch;
+ * bootstrap_func (lut.rs:49-65) = tfhe_lut_generate + this. */
+int tfhe_batch_bootstrap_lut(tfhe_engine *e, int lut_id, const uint32_t *in /*[count][n+1]*/,
+                             uint32_t *out /*[count][n+1]*/, size_t count);
+/* Replaces: trgsw::identity_key_switching after trlwe::sample_extract_index(.,0)
+ * (trgsw.rs:332-360, trlwe.rs:106-120) on caller-supplied TRLWE samples. */
+int tfhe_batch_extract_key_switch(tfhe_engine *e, const uint32_t *in_trlwe /*[count][2][N]*/,
+                                  uint32_t *out /*[count][n+1]*/, size_t count);
+
+/* ---- the hot path, device-resident buffers (no copies; asynchronous on the
+ *      engine stream).  Pointers are CUDA device pointers on the engine's GPU. */
+int tfhe_batch_gate_dev(tfhe_engine *e, tfhe_gate op, const uint8_t *d_ops /*NULL or [count]*/,
+                        const uint32_t *d_in_pairs, uint32_t *d_out, size_t count);
+int tfhe_batch_bootstrap_dev(tfhe_engine *e, int lut_id /*<0: cloud-key test vector*/,
+                             const uint32_t *d_in, uint32_t *d_out, size_t count, int key_switch);
+int tfhe_engine_synchronize(tfhe_engine *e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFHE_B200_H */
