@@ -1,0 +1,100 @@
+// aux.cu -- key re-layout at upload, device-side LUT generation, sample extraction.
+#include "kernels.h"
+
+namespace {
+
+// Reference TRGSWLv1FFT image (trgsw.rs:52-68; f64[n][2l][2][1024], re|im split,
+// natural bin order, x2-scaled per klemsa.rs:110-114) -> device order
+// cplx[n][2l][8 k2][2 o][64 v], scaled by 1/1024 (folds klemsa.rs:112,126,136 and
+// trgsw.rs:137-140; power-of-two scaling is exact).
+__global__ void bsk_relayout_kernel(const double *__restrict__ src, cplx *__restrict__ dst,
+                                    size_t total) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int v = idx & 63;
+  const int o = (idx >> 6) & 1;
+  const int k2 = (idx >> 7) & 7;
+  const size_t ir = idx >> 10;  // i * 2l + r
+  const int k = br::bin_of(v, k2);
+  const double *s = src + (ir * 2 + o) * br::kN;
+  dst[idx] = br::mk(s[k] * (1.0 / 1024.0), s[k + br::kHalf] * (1.0 / 1024.0));
+}
+
+// Reference KSK image (key.rs:102-122: u32[N*t*2^basebit][n+1]) -> rows padded to
+// `stride` words (zero fill) plus one trailing all-zero row.
+__global__ void ksk_relayout_kernel(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst,
+                                    uint32_t rows, uint32_t n, uint32_t stride) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = ((size_t)rows + 1) * stride;
+  if (idx >= total) return;
+  uint32_t row = (uint32_t)(idx / stride), x = (uint32_t)(idx % stride);
+  dst[idx] = (row < rows && x <= n) ? src[(size_t)row * (n + 1) + x] : 0u;
+}
+
+__device__ __forceinline__ uint32_t div_round(uint32_t a, uint32_t b) { return (a + b / 2) / b; }
+
+// lut/generator.rs:89-137 (+ encoder.rs:66-73, utils.rs:9-12): one thread per coefficient.
+__global__ void lut_generate_kernel(const uint32_t *__restrict__ f_table, uint32_t m, double scale,
+                                    uint32_t *__restrict__ tv_slot) {
+  const uint32_t N = br::kN;
+  const uint32_t i = threadIdx.x;
+  const uint32_t offset = div_round(N, 2 * m);
+  const uint32_t srci = (i + offset) % N;
+  // box x with div_round(x*N, m) <= srci < div_round((x+1)*N, m)
+  uint32_t x = (uint32_t)(((uint64_t)srci * m) / N);
+  while (x + 1 < m && div_round((x + 1) * N, m) <= srci) x++;
+  while (x > 0 && div_round(x * N, m) > srci) x--;
+  uint32_t val = 0;
+  if (div_round(x * N, m) <= srci && srci < div_round((x + 1) * N, m)) {
+    uint32_t msg = f_table[x] % m;
+    double d = fmod((double)msg * scale, 1.0) * 4294967296.0;
+    val = (uint32_t)(unsigned long long)(long long)d;
+  }
+  if (i >= N - offset) val = 0u - val;
+  tv_slot[i] = 0u;        // poly.a
+  tv_slot[N + i] = val;   // poly.b
+}
+
+// trlwe.rs:106-120 with k = 0
+__global__ void extract_kernel(const uint32_t *__restrict__ trlwe, uint32_t *__restrict__ ext,
+                               size_t count) {
+  const uint32_t N = br::kN;
+  size_t ct = blockIdx.x;
+  if (ct >= count) return;
+  const uint32_t *a = trlwe + ct * 2 * N;
+  uint32_t *o = ext + ct * (N + 1);
+  for (uint32_t x = threadIdx.x; x <= N; x += blockDim.x) {
+    uint32_t v;
+    if (x == 0) v = a[0];
+    else if (x == N) v = a[N];
+    else v = ~a[N - x];
+    o[x] = v;
+  }
+}
+
+}  // namespace
+
+cudaError_t bsk_relayout_launch(const double *src_ref, cplx *dst, uint32_t n, uint32_t l2,
+                                cudaStream_t stream) {
+  size_t total = (size_t)n * l2 * br::kChunkCplx;
+  bsk_relayout_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src_ref, dst, total);
+  return cudaGetLastError();
+}
+cudaError_t ksk_relayout_launch(const uint32_t *src_ref, uint32_t *dst, uint32_t rows, uint32_t n,
+                                uint32_t stride, cudaStream_t stream) {
+  size_t total = ((size_t)rows + 1) * stride;
+  ksk_relayout_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src_ref, dst, rows, n,
+                                                                          stride);
+  return cudaGetLastError();
+}
+cudaError_t lut_generate_launch(const uint32_t *d_f_table, uint32_t modulus, double scale,
+                                uint32_t *d_tv_slot, cudaStream_t stream) {
+  lut_generate_kernel<<<1, br::kN, 0, stream>>>(d_f_table, modulus, scale, d_tv_slot);
+  return cudaGetLastError();
+}
+cudaError_t extract_launch(const uint32_t *d_trlwe, uint32_t *d_ext, size_t count,
+                           cudaStream_t stream) {
+  if (count == 0) return cudaSuccess;
+  extract_kernel<<<(unsigned)count, 256, 0, stream>>>(d_trlwe, d_ext, count);
+  return cudaGetLastError();
+}

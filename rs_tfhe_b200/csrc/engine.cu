@@ -1,0 +1,479 @@
+// engine.cu -- the C ABI (include/tfhe_b200.h): engine handle, cloud-key upload and
+// re-layout, batch entry points.  No CPU fallback: every compute entry point
+// needs a CUDA device and fails loudly (TFHE_ERR_CUDA) without one.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "kernels.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(call)                                                                     \
+  do {                                                                               \
+    cudaError_t e_ = (call);                                                         \
+    if (e_ != cudaSuccess)                                                           \
+      return fail(TFHE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                  __FILE__, __LINE__);                                               \
+  } while (0)
+
+constexpr int kMaxLut = 64;          // test-vector slots (slot 0 = cloud-key test vector)
+constexpr size_t kChunk = 1u << 17;  // ciphertexts per internal pass (bounds scratch memory)
+
+struct Scratch {
+  void *p = nullptr;
+  size_t bytes = 0;
+  cudaError_t reserve(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+    cudaError_t e = cudaMalloc(&p, need);
+    if (e == cudaSuccess) bytes = need;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+}  // namespace
+
+struct tfhe_engine {
+  tfhe_params p{};
+  int dev = 0;
+  int num_sms = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  std::mutex mu;
+  // cloud key: one contiguous device blob = BSK | KSK | test-vector slots
+  uint8_t *blob = nullptr;
+  size_t blob_bytes = 0, off_ksk = 0, off_tv = 0;
+  bool key_loaded = false;
+  uint32_t decomp_offset = 0;
+  uint32_t ksk_rows = 0, ksk_stride = 0;
+  int n_lut = 1;
+  cplx *tw_a = nullptr, *tw_b = nullptr;
+  Scratch s_in, s_ext, s_out, s_ops, s_misc;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  float last_ms[2] = {0.f, 0.f};
+  uint64_t launches = 0;
+
+  const cplx *bsk() const { return reinterpret_cast<const cplx *>(blob); }
+  const uint32_t *ksk() const { return reinterpret_cast<const uint32_t *>(blob + off_ksk); }
+  uint32_t *tv() const { return reinterpret_cast<uint32_t *>(blob + off_tv); }
+};
+
+namespace {
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+void blob_layout(tfhe_engine *e) {
+  const tfhe_params &p = e->p;
+  e->ksk_rows = TFHE_N * p.iks_t * (1u << p.basebit);
+  e->ksk_stride = ks_stride(p.n);
+  size_t bsk_bytes = (size_t)p.n * 2 * p.l * br::kChunkCplx * sizeof(cplx);
+  size_t ksk_bytes = ((size_t)e->ksk_rows + 1) * e->ksk_stride * 4;
+  e->off_ksk = align_up(bsk_bytes, 256);
+  e->off_tv = align_up(e->off_ksk + ksk_bytes, 256);
+  e->blob_bytes = e->off_tv + (size_t)kMaxLut * 2 * TFHE_N * 4;
+}
+
+int ensure_blob(tfhe_engine *e) {
+  if (e->blob) return TFHE_OK;
+  blob_layout(e);
+  CU(cudaMalloc(reinterpret_cast<void **>(&e->blob), e->blob_bytes));
+  return TFHE_OK;
+}
+
+// One pass over <= kChunk ciphertexts already on the device.
+//   gate mode: op >= 0 or d_ops != NULL; plain mode: op < 0 and d_ops == NULL.
+//   out_kind: 0 key-switched LWE [n+1]; 1 extract_2 [n+1]; 2 TRLWE [2][N]
+int run_device(tfhe_engine *e, int op, const uint8_t *d_ops, int lut_id, const uint32_t *d_in,
+               uint32_t *d_out, size_t count, int out_kind) {
+  if (!e->key_loaded) return fail(TFHE_ERR_NO_KEY, "cloud key not loaded");
+  if (lut_id >= e->n_lut) return fail(TFHE_ERR_INVALID, "unknown lut id %d", lut_id);
+  BrArgs a{};
+  a.bsk = e->bsk();
+  a.tw_a = e->tw_a; a.tw_b = e->tw_b;
+  a.tv = e->tv(); a.tv_index = nullptr; a.tv_default = lut_id < 0 ? 0 : lut_id;
+  a.in = d_in; a.ops = d_ops; a.op = op;
+  a.n = e->p.n; a.offset = e->decomp_offset; a.count = count;
+  if (out_kind == 0) {
+    CU(e->s_ext.reserve(count * (TFHE_N + 1) * 4));
+    a.out = static_cast<uint32_t *>(e->s_ext.p);
+    a.out_mode = BR_OUT_EXTRACT;
+  } else {
+    a.out = d_out;
+    a.out_mode = out_kind == 1 ? BR_OUT_EXTRACT2 : BR_OUT_TRLWE;
+  }
+  CU(cudaEventRecord(e->ev[0], e->stream));
+  CU(br_launch(e->p.l, e->p.bgbit, a, e->num_sms, e->stream));
+  e->launches++;
+  CU(cudaEventRecord(e->ev[1], e->stream));
+  if (out_kind == 0) {
+    KsArgs k{};
+    k.ksk = e->ksk(); k.ext = static_cast<const uint32_t *>(e->s_ext.p); k.out = d_out;
+    k.n = e->p.n; k.basebit = e->p.basebit; k.iks_t = e->p.iks_t;
+    k.stride = e->ksk_stride; k.zero_row = e->ksk_rows; k.count = count;
+    CU(ks_launch(k, e->stream));
+    e->launches++;
+  }
+  CU(cudaEventRecord(e->ev[2], e->stream));
+  return TFHE_OK;
+}
+
+// Host-buffer driver: H2D -> kernels -> D2H in chunks of kChunk ciphertexts.
+int run_host(tfhe_engine *e, int op, const uint8_t *ops, int lut_id, const uint32_t *in,
+             size_t in_words, uint32_t *out, size_t out_words, size_t count, int out_kind) {
+  if (!e) return fail(TFHE_ERR_INVALID, "null engine");
+  if (count == 0) return TFHE_OK;
+  if (!in || !out) return fail(TFHE_ERR_INVALID, "null buffer");
+  std::lock_guard<std::mutex> lock(e->mu);
+  CU(cudaSetDevice(e->dev));
+  float ms0 = 0.f, ms1 = 0.f;
+  for (size_t base = 0; base < count; base += kChunk) {
+    size_t c = count - base < kChunk ? count - base : kChunk;
+    CU(e->s_in.reserve(c * in_words * 4));
+    CU(e->s_out.reserve(c * out_words * 4));
+    CU(cudaMemcpyAsync(e->s_in.p, in + base * in_words, c * in_words * 4, cudaMemcpyHostToDevice,
+                       e->stream));
+    const uint8_t *d_ops = nullptr;
+    if (ops) {
+      CU(e->s_ops.reserve(c));
+      CU(cudaMemcpyAsync(e->s_ops.p, ops + base, c, cudaMemcpyHostToDevice, e->stream));
+      d_ops = static_cast<const uint8_t *>(e->s_ops.p);
+    }
+    int rc = run_device(e, op, d_ops, lut_id, static_cast<const uint32_t *>(e->s_in.p),
+                        static_cast<uint32_t *>(e->s_out.p), c, out_kind);
+    if (rc != TFHE_OK) return rc;
+    CU(cudaMemcpyAsync(out + base * out_words, e->s_out.p, c * out_words * 4,
+                       cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    float t0 = 0.f, t1 = 0.f;
+    cudaEventElapsedTime(&t0, e->ev[0], e->ev[1]);
+    cudaEventElapsedTime(&t1, e->ev[1], e->ev[2]);
+    ms0 += t0; ms1 += t1;
+  }
+  e->last_ms[0] = ms0; e->last_ms[1] = ms1;
+  return TFHE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tfhe_abi_version(void) { return TFHE_B200_ABI_VERSION; }
+const char *tfhe_last_error(void) { return g_err; }
+
+int tfhe_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int tfhe_engine_create(const tfhe_params *params, int device_id, tfhe_engine **out) {
+  if (!params || !out) return fail(TFHE_ERR_INVALID, "null argument");
+  *out = nullptr;
+  const tfhe_params &p = *params;
+  if (p.N != TFHE_N) return fail(TFHE_ERR_INVALID, "N must be %d (got %u)", TFHE_N, p.N);
+  if (!br_supported(p.l, p.bgbit))
+    return fail(TFHE_ERR_INVALID, "unsupported gadget (l=%u, bgbit=%u)", p.l, p.bgbit);
+  if (p.n == 0 || p.n > 1216) return fail(TFHE_ERR_INVALID, "n out of range (%u)", p.n);
+  if (p.basebit == 0 || p.iks_t == 0 || p.basebit * p.iks_t > 31)
+    return fail(TFHE_ERR_INVALID, "bad key-switch parameters");
+  if (ks_stride(p.n) / 4 > 320) return fail(TFHE_ERR_INVALID, "n too large for key switch");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(TFHE_ERR_CUDA, "no CUDA device available (%s); this engine has no CPU path",
+                ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
+  }
+  if (device_id < 0 || device_id >= ndev)
+    return fail(TFHE_ERR_INVALID, "device %d out of range (have %d)", device_id, ndev);
+  CU(cudaSetDevice(device_id));
+  tfhe_engine *e = new (std::nothrow) tfhe_engine();
+  if (!e) return fail(TFHE_ERR_ALLOC, "out of host memory");
+  e->p = p;
+  e->dev = device_id;
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device_id));
+  e->num_sms = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+  e->stream = e->own_stream;
+  for (auto &ev : e->ev) CU(cudaEventCreate(&ev));
+  // twiddles (br_core.cuh): ta[r][k0] = e^{i pi r(1-4k0)/1024}, tb[j][x] = e^{-2 pi i jx/64}
+  std::vector<cplx> ta(64 * 8), tb(8 * 8);
+  for (int r = 0; r < 64; r++)
+    for (int k0 = 0; k0 < 8; k0++) {
+      int idx = ((r * (1 - 4 * k0)) % 2048 + 2048) % 2048;
+      double ang = M_PI * (double)idx / 1024.0;
+      ta[r * 8 + k0] = br::mk(std::cos(ang), std::sin(ang));
+    }
+  for (int j = 0; j < 8; j++)
+    for (int x = 0; x < 8; x++) {
+      double ang = -2.0 * M_PI * (double)((j * x) % 64) / 64.0;
+      tb[j * 8 + x] = br::mk(std::cos(ang), std::sin(ang));
+    }
+  CU(cudaMalloc(reinterpret_cast<void **>(&e->tw_a), ta.size() * sizeof(cplx)));
+  CU(cudaMalloc(reinterpret_cast<void **>(&e->tw_b), tb.size() * sizeof(cplx)));
+  CU(cudaMemcpy(e->tw_a, ta.data(), ta.size() * sizeof(cplx), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(e->tw_b, tb.data(), tb.size() * sizeof(cplx), cudaMemcpyHostToDevice));
+  blob_layout(e);
+  *out = e;
+  return TFHE_OK;
+}
+
+void tfhe_engine_destroy(tfhe_engine *e) {
+  if (!e) return;
+  cudaSetDevice(e->dev);
+  cudaDeviceSynchronize();
+  if (e->blob) cudaFree(e->blob);
+  if (e->tw_a) cudaFree(e->tw_a);
+  if (e->tw_b) cudaFree(e->tw_b);
+  e->s_in.release(); e->s_ext.release(); e->s_out.release(); e->s_ops.release(); e->s_misc.release();
+  for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
+  if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  delete e;
+}
+
+int tfhe_engine_set_stream(tfhe_engine *e, void *cuda_stream) {
+  if (!e) return fail(TFHE_ERR_INVALID, "null engine");
+  std::lock_guard<std::mutex> lock(e->mu);
+  e->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : e->own_stream;
+  return TFHE_OK;
+}
+
+uint64_t tfhe_engine_kernel_launches(const tfhe_engine *e) { return e ? e->launches : 0; }
+
+int tfhe_engine_last_kernel_ms(tfhe_engine *e, float out_ms[2]) {
+  if (!e || !out_ms) return fail(TFHE_ERR_INVALID, "null argument");
+  out_ms[0] = e->last_ms[0];
+  out_ms[1] = e->last_ms[1];
+  return TFHE_OK;
+}
+
+int tfhe_engine_load_cloud_key(tfhe_engine *e, uint32_t decomposition_offset,
+                               const uint32_t *testvec_a, const uint32_t *testvec_b,
+                               const uint32_t *ksk, const double *bsk) {
+  if (!e || !testvec_a || !testvec_b || !ksk || !bsk) return fail(TFHE_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lock(e->mu);
+  CU(cudaSetDevice(e->dev));
+  int rc = ensure_blob(e);
+  if (rc != TFHE_OK) return rc;
+  const tfhe_params &p = e->p;
+  const size_t bsk_ref_bytes = (size_t)p.n * 2 * p.l * 2 * TFHE_N * sizeof(double);
+  const size_t ksk_ref_bytes = (size_t)e->ksk_rows * (p.n + 1) * 4;
+  CU(e->s_misc.reserve(bsk_ref_bytes > ksk_ref_bytes ? bsk_ref_bytes : ksk_ref_bytes));
+  CU(cudaMemcpyAsync(e->s_misc.p, bsk, bsk_ref_bytes, cudaMemcpyHostToDevice, e->stream));
+  CU(bsk_relayout_launch(static_cast<const double *>(e->s_misc.p),
+                         reinterpret_cast<cplx *>(e->blob), p.n, 2 * p.l, e->stream));
+  CU(cudaMemcpyAsync(e->s_misc.p, ksk, ksk_ref_bytes, cudaMemcpyHostToDevice, e->stream));
+  CU(ksk_relayout_launch(static_cast<const uint32_t *>(e->s_misc.p),
+                         reinterpret_cast<uint32_t *>(e->blob + e->off_ksk), e->ksk_rows, p.n,
+                         e->ksk_stride, e->stream));
+  e->launches += 2;
+  CU(cudaMemsetAsync(e->tv(), 0, (size_t)kMaxLut * 2 * TFHE_N * 4, e->stream));
+  CU(cudaMemcpyAsync(e->tv(), testvec_a, TFHE_N * 4, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMemcpyAsync(e->tv() + TFHE_N, testvec_b, TFHE_N * 4, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  e->s_misc.release();
+  e->decomp_offset = decomposition_offset;
+  e->n_lut = 1;
+  e->key_loaded = true;
+  return TFHE_OK;
+}
+
+int tfhe_engine_alloc_cloud_key(tfhe_engine *e) {
+  if (!e) return fail(TFHE_ERR_INVALID, "null engine");
+  std::lock_guard<std::mutex> lock(e->mu);
+  CU(cudaSetDevice(e->dev));
+  return ensure_blob(e);
+}
+
+int tfhe_engine_cloud_key_blob(tfhe_engine *e, void **device_ptr, size_t *bytes) {
+  if (!e || !device_ptr || !bytes) return fail(TFHE_ERR_INVALID, "null argument");
+  if (!e->blob) return fail(TFHE_ERR_NO_KEY, "cloud key blob not allocated");
+  *device_ptr = e->blob;
+  *bytes = e->blob_bytes;
+  return TFHE_OK;
+}
+
+int tfhe_engine_commit_cloud_key(tfhe_engine *e, uint32_t decomposition_offset) {
+  if (!e) return fail(TFHE_ERR_INVALID, "null engine");
+  if (!e->blob) return fail(TFHE_ERR_NO_KEY, "cloud key blob not allocated");
+  std::lock_guard<std::mutex> lock(e->mu);
+  e->decomp_offset = decomposition_offset;
+  e->n_lut = 1;
+  e->key_loaded = true;
+  return TFHE_OK;
+}
+
+int tfhe_batch_gate(tfhe_engine *e, tfhe_gate op, const uint32_t *in_pairs, uint32_t *out,
+                    size_t count) {
+  if (!e) return fail(TFHE_ERR_INVALID, "null engine");
+  if ((int)op < 0 || (int)op >= TFHE_GATE_COUNT) return fail(TFHE_ERR_INVALID, "bad gate %d", (int)op);
+  const size_t w = e->p.n + 1;
+  return run_host(e, (int)op, nullptr, -1, in_pairs, 2 * w, out, w, count, 0);
+}
+
+int tfhe_batch_gate_mixed(tfhe_engine *e, const uint8_t *ops, const uint32_t *in_pairs,
+                          uint32_t *out, size_t count) {
+  if (!e) return fail(TFHE_ERR_INVALID, "null engine");
+  if (!ops && count) return fail(TFHE_ERR_INVALID, "null ops");
+  for (size_t i = 0; i < count; i++)
+    if (ops[i] >= TFHE_GATE_COUNT) return fail(TFHE_ERR_INVALID, "bad gate %d at %zu", ops[i], i);
+  const size_t w = e->p.n + 1;
+  return run_host(e, 0, ops, -1, in_pairs, 2 * w, out, w, count, 0);
+}
+
+int tfhe_batch_bootstrap(tfhe_engine *e, const uint32_t *in, uint32_t *out, size_t count,
+                         int key_switch) {
+  if (!e) return fail(TFHE_ERR_INVALID, "null engine");
+  const size_t w = e->p.n + 1;
+  return run_host(e, -1, nullptr, -1, in, w, out, w, count, key_switch ? 0 : 1);
+}
+
+int tfhe_batch_blind_rotate(tfhe_engine *e, const uint32_t *in, uint32_t *out_trlwe, size_t count) {
+  if (!e) return fail(TFHE_ERR_INVALID, "null engine");
+  return run_host(e, -1, nullptr, -1, in, e->p.n + 1, out_trlwe, 2 * TFHE_N, count, 2);
+}
+
+int tfhe_lut_register(tfhe_engine *e, const uint32_t *poly_a, const uint32_t *poly_b,
+                      int *lut_id_out) {
+  if (!e || !poly_b || !lut_id_out) return fail(TFHE_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (!e->blob) return fail(TFHE_ERR_NO_KEY, "cloud key not loaded");
+  if (e->n_lut >= kMaxLut) return fail(TFHE_ERR_ALLOC, "out of LUT slots (%d)", kMaxLut);
+  CU(cudaSetDevice(e->dev));
+  uint32_t *slot = e->tv() + (size_t)e->n_lut * 2 * TFHE_N;
+  if (poly_a) CU(cudaMemcpyAsync(slot, poly_a, TFHE_N * 4, cudaMemcpyHostToDevice, e->stream));
+  else CU(cudaMemsetAsync(slot, 0, TFHE_N * 4, e->stream));
+  CU(cudaMemcpyAsync(slot + TFHE_N, poly_b, TFHE_N * 4, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  *lut_id_out = e->n_lut++;
+  return TFHE_OK;
+}
+
+int tfhe_lut_generate(tfhe_engine *e, const uint32_t *f_table, uint32_t modulus, double scale,
+                      uint32_t *lut_b_out, int *lut_id_out) {
+  if (!e || !f_table || !lut_id_out) return fail(TFHE_ERR_INVALID, "null argument");
+  if (modulus == 0 || modulus > TFHE_N) return fail(TFHE_ERR_INVALID, "bad modulus %u", modulus);
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (!e->blob) return fail(TFHE_ERR_NO_KEY, "cloud key not loaded");
+  if (e->n_lut >= kMaxLut) return fail(TFHE_ERR_ALLOC, "out of LUT slots (%d)", kMaxLut);
+  CU(cudaSetDevice(e->dev));
+  if (scale <= 0.0) scale = 1.0 / (2.0 * (double)modulus);  // lut/encoder.rs:36
+  CU(e->s_misc.reserve((size_t)modulus * 4));
+  CU(cudaMemcpyAsync(e->s_misc.p, f_table, (size_t)modulus * 4, cudaMemcpyHostToDevice, e->stream));
+  uint32_t *slot = e->tv() + (size_t)e->n_lut * 2 * TFHE_N;
+  CU(lut_generate_launch(static_cast<const uint32_t *>(e->s_misc.p), modulus, scale, slot, e->stream));
+  e->launches++;
+  if (lut_b_out)
+    CU(cudaMemcpyAsync(lut_b_out, slot + TFHE_N, TFHE_N * 4, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  *lut_id_out = e->n_lut++;
+  return TFHE_OK;
+}
+
+int tfhe_batch_bootstrap_lut(tfhe_engine *e, int lut_id, const uint32_t *in, uint32_t *out,
+                             size_t count) {
+  if (!e) return fail(TFHE_ERR_INVALID, "null engine");
+  if (lut_id < 0 || lut_id >= e->n_lut) return fail(TFHE_ERR_INVALID, "unknown lut id %d", lut_id);
+  const size_t w = e->p.n + 1;
+  return run_host(e, -1, nullptr, lut_id, in, w, out, w, count, 0);
+}
+
+int tfhe_batch_extract_key_switch(tfhe_engine *e, const uint32_t *in_trlwe, uint32_t *out,
+                                  size_t count) {
+  if (!e) return fail(TFHE_ERR_INVALID, "null engine");
+  if (count == 0) return TFHE_OK;
+  if (!in_trlwe || !out) return fail(TFHE_ERR_INVALID, "null buffer");
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (!e->key_loaded) return fail(TFHE_ERR_NO_KEY, "cloud key not loaded");
+  CU(cudaSetDevice(e->dev));
+  const size_t w = e->p.n + 1;
+  for (size_t base = 0; base < count; base += kChunk) {
+    size_t c = count - base < kChunk ? count - base : kChunk;
+    CU(e->s_in.reserve(c * 2 * TFHE_N * 4));
+    CU(e->s_ext.reserve(c * (TFHE_N + 1) * 4));
+    CU(e->s_out.reserve(c * w * 4));
+    CU(cudaMemcpyAsync(e->s_in.p, in_trlwe + base * 2 * TFHE_N, c * 2 * TFHE_N * 4,
+                       cudaMemcpyHostToDevice, e->stream));
+    CU(extract_launch(static_cast<const uint32_t *>(e->s_in.p), static_cast<uint32_t *>(e->s_ext.p),
+                      c, e->stream));
+    KsArgs k{};
+    k.ksk = e->ksk(); k.ext = static_cast<const uint32_t *>(e->s_ext.p);
+    k.out = static_cast<uint32_t *>(e->s_out.p);
+    k.n = e->p.n; k.basebit = e->p.basebit; k.iks_t = e->p.iks_t;
+    k.stride = e->ksk_stride; k.zero_row = e->ksk_rows; k.count = c;
+    CU(ks_launch(k, e->stream));
+    e->launches += 2;
+    CU(cudaMemcpyAsync(out + base * w, e->s_out.p, c * w * 4, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+  }
+  return TFHE_OK;
+}
+
+int tfhe_batch_gate_dev(tfhe_engine *e, tfhe_gate op, const uint8_t *d_ops,
+                        const uint32_t *d_in_pairs, uint32_t *d_out, size_t count) {
+  if (!e) return fail(TFHE_ERR_INVALID, "null engine");
+  if (!d_ops && ((int)op < 0 || (int)op >= TFHE_GATE_COUNT))
+    return fail(TFHE_ERR_INVALID, "bad gate %d", (int)op);
+  if (count == 0) return TFHE_OK;
+  std::lock_guard<std::mutex> lock(e->mu);
+  CU(cudaSetDevice(e->dev));
+  const size_t w = e->p.n + 1;
+  for (size_t base = 0; base < count; base += kChunk) {
+    size_t c = count - base < kChunk ? count - base : kChunk;
+    int rc = run_device(e, d_ops ? 0 : (int)op, d_ops ? d_ops + base : nullptr, -1,
+                        d_in_pairs + base * 2 * w, d_out + base * w, c, 0);
+    if (rc != TFHE_OK) return rc;
+  }
+  return TFHE_OK;
+}
+
+int tfhe_batch_bootstrap_dev(tfhe_engine *e, int lut_id, const uint32_t *d_in, uint32_t *d_out,
+                             size_t count, int key_switch) {
+  if (!e) return fail(TFHE_ERR_INVALID, "null engine");
+  if (count == 0) return TFHE_OK;
+  std::lock_guard<std::mutex> lock(e->mu);
+  CU(cudaSetDevice(e->dev));
+  const size_t w = e->p.n + 1;
+  for (size_t base = 0; base < count; base += kChunk) {
+    size_t c = count - base < kChunk ? count - base : kChunk;
+    int rc = run_device(e, -1, nullptr, lut_id, d_in + base * w, d_out + base * w, c,
+                        key_switch ? 0 : 1);
+    if (rc != TFHE_OK) return rc;
+  }
+  return TFHE_OK;
+}
+
+int tfhe_engine_synchronize(tfhe_engine *e) {
+  if (!e) return fail(TFHE_ERR_INVALID, "null engine");
+  CU(cudaSetDevice(e->dev));
+  CU(cudaStreamSynchronize(e->stream));
+  float t0 = 0.f, t1 = 0.f;
+  if (cudaEventElapsedTime(&t0, e->ev[0], e->ev[1]) == cudaSuccess &&
+      cudaEventElapsedTime(&t1, e->ev[1], e->ev[2]) == cudaSuccess) {
+    e->last_ms[0] = t0; e->last_ms[1] = t1;
+  } else {
+    cudaGetLastError();
+  }
+  return TFHE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,52 @@
+// kernels.h -- internal launch interface between engine.cu and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/tfhe_b200.h"
+#include "br_core.cuh"
+
+enum { BR_OUT_TRLWE = 0, BR_OUT_EXTRACT = 1, BR_OUT_EXTRACT2 = 2 };
+
+// K0+K3 (blind_rotate.cu)
+struct BrArgs {
+  const cplx *bsk;          // device order: cplx[n][2l][8][2][64] (br_core.cuh)
+  const cplx *tw_a;         // [64][8]
+  const cplx *tw_b;         // [8][8]
+  const uint32_t *tv;       // test vectors u32[slot][2][N]; slot 0 = cloud-key test vector
+  const int32_t *tv_index;  // per-ciphertext slot, or NULL -> tv_default
+  int tv_default;
+  const uint32_t *in;       // op>=0 or ops: [count][2][n+1]; else [count][n+1]
+  const uint8_t *ops;       // per-ciphertext gate or NULL
+  int op;                   // gate for all, or -1: plain bootstrap of `in`
+  uint32_t *out;            // per out_mode: [count][2][N] | [count][N+1] | [count][n+1]
+  int out_mode;
+  uint32_t n;
+  uint32_t offset;          // CloudKey.decomposition_offset, used verbatim
+  size_t count;
+};
+bool br_supported(uint32_t l, uint32_t bgbit);
+cudaError_t br_launch(uint32_t l, uint32_t bgbit, const BrArgs &args, int num_sms,
+                      cudaStream_t stream);
+
+// K4 (keyswitch.cu)
+struct KsArgs {
+  const uint32_t *ksk;   // device order: u32[rows+1][stride]; last row = zeros
+  const uint32_t *ext;   // [count][N+1] extracted level-1 samples
+  uint32_t *out;         // [count][n+1]
+  uint32_t n, basebit, iks_t, stride, zero_row;
+  size_t count;
+};
+cudaError_t ks_launch(const KsArgs &args, cudaStream_t stream);
+static inline uint32_t ks_stride(uint32_t n) { return (n + 1 + 3) & ~3u; }
+
+// layout / small kernels (aux.cu)
+cudaError_t bsk_relayout_launch(const double *src_ref, cplx *dst, uint32_t n, uint32_t l2,
+                                cudaStream_t stream);
+cudaError_t ksk_relayout_launch(const uint32_t *src_ref, uint32_t *dst, uint32_t rows, uint32_t n,
+                                uint32_t stride, cudaStream_t stream);
+cudaError_t lut_generate_launch(const uint32_t *d_f_table, uint32_t modulus, double scale,
+                                uint32_t *d_tv_slot, cudaStream_t stream);
+cudaError_t extract_launch(const uint32_t *d_trlwe, uint32_t *d_ext, size_t count,
+                           cudaStream_t stream);
