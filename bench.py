@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- bootstrapped NAND gates/s (SECURITY_128_BIT) on N B200s.
+
+A step = one pass of the hot path (gates::batch_nand: prep -> blind rotation ->
+sample extract -> key switch) over one batch of synthetic ciphertexts.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--count C] [--params 128]
+  python bench.py --impl reference ...     # CPU arm: the oracle port on host cores
+
+N>1 is launched by the driver with torch.distributed.run (one rank per GPU).
+Prints ONE JSON line on rank 0.  `value`: inputs resident in HBM, device-timed.
+`e2e`: the same metric through the host-buffer C-ABI call (tfhe_batch_gate) with
+H2D/D2H inside the timed region.  See DESIGN.md section "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "bootstrapped_nand_gates_per_sec_128bit"
+UNIT = "gates/s"
+N = 1024
+
+
+def flop_per_pbs(n: int, l: int) -> float:
+    """n*[(2l+2)*(5*(N/2)*log2(N/2) + 6*(N/2)) + 2l*2*(N/2)*8]."""
+    h = N // 2
+    return n * ((2 * l + 2) * (5 * h * 9 + 6 * h) + 2 * l * 2 * h * 8)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--count", type=int, default=65536, help="gates per GPU per step")
+    ap.add_argument("--params", default="128")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="gates in the CPU sample (0: auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(params: str, count: int) -> str:
+    return (f"gates::batch_nand, SECURITY_{params.upper()}_BIT, {count} gates per GPU per step "
+            f"(BASELINE configs[0] shape at a throughput batch size)")
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, pw = [], [], []
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2])); pw.append(float(parts[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        top = max(sm)
+        load = [x for x in sm if x >= 0.5 * top]
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "power_w_max": max(pw), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_leg(params: str, sample: int, threads: int = 0, engine=None):
+    """The oracle port (C restatement of rs-tfhe's Rayon path; rs-tfhe itself cannot be
+    built here: no cargo/rustc) timed on the host cores over a bounded sample of the same
+    workload.  If `engine` is given the sample is also pushed through the GPU path with
+    the oracle's (real) key and compared word for word -- the oracle acting as checker."""
+    import oracle as O
+
+    cores = O.max_threads() if threads <= 0 else threads
+    K = O.Keys(params, seed=0x5EED0001)
+    if sample <= 0:
+        sample = cores * 4
+        r = np.random.default_rng(5)
+        probe = r.integers(0, 2**32, (cores * 2, 2, K.params.n + 1), dtype=np.uint32)
+        t = time.perf_counter()
+        K.batch_gate(0, probe, threads=cores)
+        per = (time.perf_counter() - t) / (cores * 2)
+        sample = int(max(cores * 4, min(cores * 512, 12.0 / per)))
+        sample -= sample % cores
+    r = np.random.default_rng(6)
+    pairs = r.integers(0, 2**32, (sample, 2, K.params.n + 1), dtype=np.uint32)
+    t = time.perf_counter()
+    ref = K.batch_gate(0, pairs, threads=cores)
+    dt = time.perf_counter() - t
+    out = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": f"{sample} random-ciphertext NAND gates of the same workload, "
+                     f"{cores} OpenMP threads (one ciphertext per task, like par_map)",
+           "seconds": dt, "ms_per_gate_per_core": dt * cores / sample * 1e3}
+    if engine is not None:
+        import rs_tfhe_b200 as T
+        ck = T.CloudKey(T.PARAMS_BY_NAME[params], K.offset, K.tv_a, K.tv_b, K.ksk, K.bsk)
+        engine.load_cloud_key(ck)
+        got = engine.batch_gate("NAND", pairs)
+        out["parity_mismatch_words"] = int((got != ref).sum())
+        out["parity_checked_gates"] = sample
+    return out
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle as O
+    cores = O.max_threads()
+    K = O.Keys(args.params, seed=0x5EED0001)
+    sample = args.cpu_sample or cores * 8
+    r = np.random.default_rng(7)
+    pairs = r.integers(0, 2**32, (sample, 2, K.params.n + 1), dtype=np.uint32)
+    for _ in range(args.warmup):
+        K.batch_gate(0, pairs[:cores], threads=cores)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        K.batch_gate(0, pairs, threads=cores)
+    dt = time.perf_counter() - t
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args.params, args.count), "params": args.params,
+                   "count_per_gpu": args.count,
+                   "note": "CPU arm: C restatement of rs-tfhe's Rayon path (oracle/, kind=port; the "
+                           "Rust crate cannot be built in this image), all host threads; each step "
+                           "is a bounded sample of the workload"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} NAND gates per step x {args.steps} steps"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def synthetic_cloud_key(T, P, seed: int):
+    """Random key material in the reference's layout.  The data path is value-independent
+    (no branch depends on key values), so throughput equals that of a real key; real keys
+    are used by tests/, smoke() and the cpu_baseline parity check."""
+    r = np.random.default_rng(seed)
+    ksk = r.integers(0, 2**32, (P.ksk_rows, P.n + 1), dtype=np.uint32)
+    bsk = r.standard_normal((P.n, 2 * P.l, 2, N)) * 2.0**35
+    tv_a = np.zeros(N, dtype=np.uint32)
+    tv_b = np.full(N, 0x20000000, dtype=np.uint32)
+    offset = sum((1 << (P.bgbit - 1)) << (32 - (i + 1) * P.bgbit) for i in range(P.l)) & 0xFFFFFFFF
+    return T.CloudKey(P, offset, tv_a, tv_b, ksk, bsk)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import rs_tfhe_b200 as T
+    from rs_tfhe_b200.dist import broadcast_cloud_key
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    P = T.PARAMS_BY_NAME[args.params]
+    w = P.n + 1
+    count = args.count
+    eng = T.CudaBootstrap(P, local)
+    stream = torch.cuda.Stream(device=dev)
+    eng.set_stream(stream.cuda_stream)
+
+    # ---- cloud key: rank 0 uploads + re-lays out, the rest receive one NCCL broadcast
+    t0 = time.perf_counter()
+    ck = synthetic_cloud_key(T, P, 1234) if rank == 0 else None
+    key_bcast_ms = None
+    if world > 1:
+        with torch.cuda.stream(stream):
+            key_bcast_ms = broadcast_cloud_key(eng, ck)
+    else:
+        eng.load_cloud_key(ck)
+    key_load_s = time.perf_counter() - t0
+
+    # ---- synthetic ciphertexts (uniform random u32), pinned on the host, resident copy in HBM
+    g = torch.Generator().manual_seed(100 + rank)
+    h_in = torch.randint(-2**31, 2**31 - 1, (count, 2, w), dtype=torch.int32, generator=g).pin_memory()
+    h_out = torch.empty((count, w), dtype=torch.int32).pin_memory()
+    d_in = h_in.to(dev)
+    d_out = torch.empty((count, w), dtype=torch.int32, device=dev)
+    np_in = h_in.numpy().view(np.uint32)
+    np_out = h_out.numpy().view(np.uint32)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_dev():
+        eng.batch_gate_dev("NAND", d_in.data_ptr(), d_out.data_ptr(), count)
+
+    lib = T._load()
+    import ctypes as C
+
+    def step_host():
+        rc = lib.tfhe_batch_gate(eng._h, 0, np_in.ctypes.data_as(C.c_void_p),
+                                 np_out.ctypes.data_as(C.c_void_p), count)
+        if rc != 0:
+            raise T.EngineError(lib.tfhe_last_error().decode())
+
+    # ---- device-resident leg
+    for _ in range(args.warmup):
+        step_dev()
+    eng.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    barrier()
+    launches0 = eng.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    br_ms, ks_ms = [], []
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_dev()
+        eng.synchronize()              # also latches the per-kernel event times of this step
+        b, k = eng.last_kernel_ms()
+        br_ms.append(b); ks_ms.append(k)
+    ev1.record(stream)
+    barrier()
+    launches = eng.kernel_launches - launches0
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if sampler else None
+
+    # ---- end-to-end leg: host buffers through the C ABI (H2D + kernels + D2H per step)
+    for _ in range(min(args.warmup, 2)):
+        step_host()
+    barrier()
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t
+    barrier()
+    result_checksum = int(np_out[:, -1].astype(np.uint64).sum() & 0xFFFFFFFF)
+
+    if world > 1:
+        tt = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total, e2e_ms = float(tt[0]), float(tt[1])
+    else:
+        e2e_ms = e2e_s * 1e3
+
+    if rank == 0:
+        total = count * world * args.steps
+        value = total / (ms_total * 1e-3)
+        br_avg = sum(br_ms) / len(br_ms)
+        ks_avg = sum(ks_ms) / len(ks_ms)
+        flops = flop_per_pbs(P.n, P.l) * count
+        fp64_peak = eng.probe_fp64_tflops()
+        achieved = flops / (br_avg * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("blind_rotate_dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        hbm_peak = 6552.0
+        try:
+            hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+            hbm_src = "MEASURED_PEAKS.json"
+        except Exception:
+            hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+        # compulsory bytes of one blind-rotation launch: 2 LWE in + extracted sample out per gate
+        # plus the Fourier BSK once per launch (it is re-served from L2 after that)
+        bsk_bytes = P.n * 2 * P.l * 2 * N * 8
+        br_bytes = count * (2 * w * 4 + (N + 1) * 4) + bsk_bytes
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": workload_name(args.params, count), "params": args.params,
+                "count_per_gpu": count, "n": P.n, "l": P.l, "bgbit": P.bgbit,
+                "l2": f"inputs {count * 2 * w * 4 / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
+                "inputs": "uniform random u32 LWE pairs and random key material (value-independent data path)",
+                "us_per_pbs": ms_total / args.steps * 1e3 / count,
+            },
+            "e2e": {"value": total / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(count * 2 * w * 4),
+                    "d2h_bytes_per_step": int(count * w * 4),
+                    "api": "tfhe_batch_gate (C ABI, pinned host buffers)",
+                    "result_checksum": result_checksum},
+            "gpu_launches": int(launches),
+            "kernels_ms_per_step": {"blind_rotate": br_avg, "key_switch": ks_avg},
+            "roofline": {
+                "kernel": "blind_rotate_kernel", "bound": "fp64", "achieved": achieved,
+                "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                "traffic": traffic,
+                "peak_source": "DFMA probe kernel measured in this run (tfhe_probe_fp64_tflops); "
+                               "MEASURED_PEAKS.json holds no FP64 figure; nominal 148 SM x 64 FMA x 2 "
+                               "x 1.965 GHz = 37.2 TFLOP/s",
+                "algorithmic_flop_per_launch": flops,
+                "hbm_view": {"bound": "hbm", "achieved": br_bytes / (br_avg * 1e-3) / 1e9,
+                             "peak": hbm_peak, "unit": "GB/s",
+                             "frac": br_bytes / (br_avg * 1e-3) / 1e9 / hbm_peak,
+                             "peak_source": hbm_src, "algorithmic_bytes_per_launch": br_bytes},
+            },
+            "clocks": clocks,
+            "key_load_s": key_load_s, "key_broadcast_ms": key_bcast_ms,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_leg(args.params, args.cpu_sample, engine=eng)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -92,6 +92,10 @@ uint64_t tfhe_engine_kernel_launches(const tfhe_engine *e);
  * [1]=key switch, measured with CUDA events on the engine stream. */
 int tfhe_engine_last_kernel_ms(tfhe_engine *e, float out_ms[2]);
 
+/* Diagnostic (roofline denominator): sustained FP64 FMA rate of the engine's GPU,
+ * measured now with a register-only DFMA kernel; TFLOP/s (2 flop per FMA). */
+int tfhe_probe_fp64_tflops(tfhe_engine *e, double *tflops_out);
+
 /* ---- cloud key ----------------------------------------------------------- */
 /* Replaces: the CloudKey a caller passes to every gate (key.rs:51-56).  Takes
  * the reference's memory images and re-lays them out on the device once:

@@ -23,7 +23,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(_CSRC, "libtfhe_b200.so")
+LIB_PATH = os.environ.get("TFHE_B200_LIB") or os.path.join(_CSRC, "libtfhe_b200.so")
 N = 1024
 
 __all__ = [
@@ -147,6 +147,7 @@ def _load():
     L.tfhe_batch_gate_dev.argtypes = [vp, C.c_int, vp, vp, vp, C.c_size_t]
     L.tfhe_batch_bootstrap_dev.argtypes = [vp, C.c_int, vp, vp, C.c_size_t, C.c_int]
     L.tfhe_engine_synchronize.argtypes = [vp]
+    L.tfhe_probe_fp64_tflops.argtypes = [vp, C.POINTER(C.c_double)]
     if L.tfhe_abi_version() != 1:
         raise EngineError("libtfhe_b200.so ABI version mismatch")
     _lib = L
@@ -265,6 +266,12 @@ class CudaBootstrap:
         ms = (C.c_float * 2)()
         _check(_load().tfhe_engine_last_kernel_ms(self._h, ms))
         return float(ms[0]), float(ms[1])
+
+    def probe_fp64_tflops(self) -> float:
+        """Measured DFMA rate of this GPU (roofline denominator for the FP64-bound kernel)."""
+        v = C.c_double(0.0)
+        _check(_load().tfhe_probe_fp64_tflops(self._h, C.byref(v)))
+        return v.value
 
     # ---- Bootstrap trait (batched: accepts [n+1] or [count][n+1])
     def bootstrap(self, ctxt, cloud_key: Optional[CloudKey] = None):

@@ -72,7 +72,30 @@ __global__ void extract_kernel(const uint32_t *__restrict__ trlwe, uint32_t *__r
   }
 }
 
+// Roofline denominator: sustained DFMA rate of this GPU right now (8 independent
+// chains per thread, no memory traffic).  Diagnostic only -- never on the hot path.
+__global__ void fp64_probe_kernel(double *sink, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+  double a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 0.999999999, c = 1e-12;
+#pragma unroll 1
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+      a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+  }
+  double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (r == 123.456) sink[0] = r;  // never true; keeps the chains alive
+}
+
 }  // namespace
+
+cudaError_t fp64_probe_launch(double *d_sink, int blocks, int iters, cudaStream_t stream) {
+  fp64_probe_kernel<<<blocks, 256, 0, stream>>>(d_sink, iters);
+  return cudaGetLastError();
+}
 
 cudaError_t bsk_relayout_launch(const double *src_ref, cplx *dst, uint32_t n, uint32_t l2,
                                 cudaStream_t stream) {

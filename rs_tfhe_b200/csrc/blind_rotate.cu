@@ -21,6 +21,13 @@
 
 using namespace br;
 
+#ifndef BR_PRODUCER_SLEEP_NS
+#define BR_PRODUCER_SLEEP_NS 256
+#endif
+#ifndef BR_STAGGER_NS
+#define BR_STAGGER_NS 0
+#endif
+
 namespace {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -36,6 +43,22 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// producer-side wait: back off between polls so the spin does not steal issue slots
+// from the consumer warps sharing its SM sub-partition
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(BR_PRODUCER_SLEEP_NS);
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   uint32_t ok;
@@ -118,7 +141,7 @@ __global__ void __launch_bounds__(G * 64 + 128, 1) blind_rotate_kernel(const BrA
       const uint32_t rows = n * L2;
       for (uint32_t rd = 0; rd < rounds; rd++) {
         for (uint32_t row = 0; row < rows; row++) {
-          mbar_wait(&empty[stage], parity ^ 1);
+          mbar_wait_backoff(&empty[stage], parity ^ 1);
           mbar_arrive_expect_tx(&full[stage], kStageBytes);
           tma_load_1d(reinterpret_cast<uint8_t *>(ring) + stage * kStageBytes,
                       src0 + (size_t)row * kStageBytes, kStageBytes, &full[stage]);
@@ -177,6 +200,7 @@ __global__ void __launch_bounds__(G * 64 + 128, 1) blind_rotate_kernel(const BrA
         acc[x] = rot_coeff(tv + (x & ~(kN - 1)), x & (kN - 1), b_tilda);
     }
     group_sync(g);
+    if (BR_STAGGER_NS > 0 && rd == 0) __nanosleep(g * BR_STAGGER_NS);
 
     for (uint32_t i = 0; i < n; i++) {
       cplx racc[2][8];

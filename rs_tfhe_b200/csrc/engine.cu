@@ -266,6 +266,29 @@ int tfhe_engine_last_kernel_ms(tfhe_engine *e, float out_ms[2]) {
   return TFHE_OK;
 }
 
+int tfhe_probe_fp64_tflops(tfhe_engine *e, double *tflops_out) {
+  if (!e || !tflops_out) return fail(TFHE_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lock(e->mu);
+  CU(cudaSetDevice(e->dev));
+  CU(e->s_misc.reserve(64));
+  const int blocks = e->num_sms * 8, iters = 1 << 15;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; rep++) {
+    CU(cudaEventRecord(e->ev[3], e->stream));
+    CU(fp64_probe_launch(static_cast<double *>(e->s_misc.p), blocks, iters, e->stream));
+    CU(cudaEventRecord(e->ev[2], e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e->ev[3], e->ev[2]));
+    double flops = (double)blocks * 256.0 * (double)iters * 32.0 * 2.0;
+    double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  e->launches += 4;
+  *tflops_out = best;
+  return TFHE_OK;
+}
+
 int tfhe_engine_load_cloud_key(tfhe_engine *e, uint32_t decomposition_offset,
                                const uint32_t *testvec_a, const uint32_t *testvec_b,
                                const uint32_t *ksk, const double *bsk) {

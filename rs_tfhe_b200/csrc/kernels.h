@@ -50,3 +50,4 @@ cudaError_t lut_generate_launch(const uint32_t *d_f_table, uint32_t modulus, dou
                                 uint32_t *d_tv_slot, cudaStream_t stream);
 cudaError_t extract_launch(const uint32_t *d_trlwe, uint32_t *d_ext, size_t count,
                            cudaStream_t stream);
+cudaError_t fp64_probe_launch(double *d_sink, int blocks, int iters, cudaStream_t stream);
