@@ -1,0 +1,142 @@
+//! `rs_tfhe::cuda` -- thin FFI over include/tfhe_b200.h.
+//!
+//! * `CudaBootstrap` implements `bootstrap::Bootstrap` (src/bootstrap/mod.rs:23-38), the slot
+//!   examples/bootstrap_strategies.rs:94-97 reserves for `"gpu"`.
+//! * `batch_*` mirror gates::batch_*[_with_railgun] (src/gates.rs:352-547) and
+//!   trgsw::batch_blind_rotate (src/trgsw.rs:289-305).
+//! * `LutBootstrap::bootstrap_lut` / `bootstrap_func` (src/bootstrap/lut.rs:49-99) get a batched
+//!   device path.
+//!
+//! Lives inside the crate because `TRGSWLv1FFT.trlwe_fft` is private (src/trgsw.rs:53-55); the
+//! bootstrapping key is passed as the plain nested array it is:
+//! `[TRGSWLv1FFT; n]` == `f64[n][2l][2][1024]`.
+use std::os::raw::{c_char, c_double, c_int, c_void};
+
+use crate::bootstrap::Bootstrap;
+use crate::key::CloudKey;
+use crate::params;
+use crate::trlwe::TRLWELv1;
+use crate::utils::Ciphertext;
+
+#[repr(C)]
+struct TfheParams { n: u32, big_n: u32, l: u32, bgbit: u32, basebit: u32, iks_t: u32 }
+#[repr(C)]
+pub struct TfheEngine { _private: [u8; 0] }
+
+#[link(name = "tfhe_b200")]
+extern "C" {
+    fn tfhe_last_error() -> *const c_char;
+    fn tfhe_engine_create(p: *const TfheParams, device: c_int, out: *mut *mut TfheEngine) -> c_int;
+    fn tfhe_engine_destroy(e: *mut TfheEngine);
+    fn tfhe_engine_load_cloud_key(e: *mut TfheEngine, decomposition_offset: u32,
+        testvec_a: *const u32, testvec_b: *const u32, ksk: *const u32, bsk: *const c_double) -> c_int;
+    fn tfhe_batch_gate(e: *mut TfheEngine, op: c_int, in_pairs: *const u32, out: *mut u32, count: usize) -> c_int;
+    fn tfhe_batch_bootstrap(e: *mut TfheEngine, input: *const u32, out: *mut u32, count: usize, key_switch: c_int) -> c_int;
+    fn tfhe_batch_blind_rotate(e: *mut TfheEngine, input: *const u32, out_trlwe: *mut u32, count: usize) -> c_int;
+    fn tfhe_lut_generate(e: *mut TfheEngine, f_table: *const u32, modulus: u32, scale: c_double,
+        lut_b_out: *mut u32, lut_id_out: *mut c_int) -> c_int;
+    fn tfhe_batch_bootstrap_lut(e: *mut TfheEngine, lut_id: c_int, input: *const u32, out: *mut u32, count: usize) -> c_int;
+}
+
+#[derive(Copy, Clone)]
+#[repr(i32)]
+pub enum Gate { Nand = 0, And = 1, Or = 2, Xor = 3, Xnor = 4, Nor = 5, AndNy = 6, AndYn = 7, OrNy = 8, OrYn = 9 }
+
+fn check(rc: c_int) {
+    if rc != 0 {
+        let msg = unsafe { std::ffi::CStr::from_ptr(tfhe_last_error()) }.to_string_lossy().into_owned();
+        panic!("tfhe_b200: {}", msg); // the reference's error model is panic (unwrap everywhere)
+    }
+}
+
+/// One engine per (process, GPU); the cloud key stays resident on the device.
+pub struct CudaBootstrap { raw: *mut TfheEngine, loaded_key: std::sync::Mutex<usize> }
+unsafe impl Send for CudaBootstrap {}
+unsafe impl Sync for CudaBootstrap {} // calls are serialised inside the engine
+
+impl CudaBootstrap {
+    pub fn new(device: i32) -> Self {
+        let p = TfheParams {
+            n: params::tlwe_lv0::N as u32, big_n: params::trgsw_lv1::N as u32,
+            l: params::trgsw_lv1::L as u32, bgbit: params::trgsw_lv1::BGBIT,
+            basebit: params::trgsw_lv1::BASEBIT as u32, iks_t: params::trgsw_lv1::IKS_T as u32,
+        };
+        let mut raw = std::ptr::null_mut();
+        check(unsafe { tfhe_engine_create(&p, device, &mut raw) });
+        CudaBootstrap { raw, loaded_key: std::sync::Mutex::new(0) }
+    }
+
+    /// Upload `ck` once (identity = address of the key the caller keeps alive).
+    fn bind(&self, ck: &CloudKey) {
+        let id = ck as *const CloudKey as usize;
+        let mut cur = self.loaded_key.lock().unwrap();
+        if *cur != id {
+            check(unsafe {
+                tfhe_engine_load_cloud_key(self.raw, ck.decomposition_offset,
+                    ck.blind_rotate_testvec.a.as_ptr(), ck.blind_rotate_testvec.b.as_ptr(),
+                    ck.key_switching_key.as_ptr() as *const u32,      // Vec<TLWELv0{p:[u32;n+1]}>
+                    ck.bootstrapping_key.as_ptr() as *const c_double) // Vec<TRGSWLv1FFT> = f64[n][2l][2][1024]
+            });
+            *cur = id;
+        }
+    }
+
+    pub fn batch_gate(&self, op: Gate, inputs: &[(Ciphertext, Ciphertext)], ck: &CloudKey) -> Vec<Ciphertext> {
+        self.bind(ck);
+        let mut out = vec![Ciphertext::new(); inputs.len()];
+        check(unsafe { tfhe_batch_gate(self.raw, op as c_int, inputs.as_ptr() as *const u32,
+                                       out.as_mut_ptr() as *mut u32, inputs.len()) });
+        out
+    }
+
+    pub fn batch_blind_rotate(&self, srcs: &[Ciphertext], ck: &CloudKey) -> Vec<TRLWELv1> {
+        self.bind(ck);
+        let mut out = vec![TRLWELv1::new(); srcs.len()];
+        check(unsafe { tfhe_batch_blind_rotate(self.raw, srcs.as_ptr() as *const u32,
+                                               out.as_mut_ptr() as *mut u32, srcs.len()) });
+        out
+    }
+
+    /// LutBootstrap::bootstrap_func over a batch: the closure is tabulated on the host.
+    pub fn batch_bootstrap_func<F: Fn(usize) -> usize>(&self, cts: &[Ciphertext], f: F,
+                                                       message_modulus: usize, ck: &CloudKey) -> Vec<Ciphertext> {
+        self.bind(ck);
+        let table: Vec<u32> = (0..message_modulus).map(|x| f(x) as u32).collect();
+        let mut id: c_int = -1;
+        check(unsafe { tfhe_lut_generate(self.raw, table.as_ptr(), message_modulus as u32, 0.0,
+                                         std::ptr::null_mut(), &mut id) });
+        let mut out = vec![Ciphertext::new(); cts.len()];
+        check(unsafe { tfhe_batch_bootstrap_lut(self.raw, id, cts.as_ptr() as *const u32,
+                                                out.as_mut_ptr() as *mut u32, cts.len()) });
+        out
+    }
+}
+
+impl Drop for CudaBootstrap {
+    fn drop(&mut self) { unsafe { tfhe_engine_destroy(self.raw) } }
+}
+
+impl Bootstrap for CudaBootstrap {
+    fn bootstrap(&self, ctxt: &Ciphertext, cloud_key: &CloudKey) -> Ciphertext {
+        self.bind(cloud_key);
+        let mut out = Ciphertext::new();
+        check(unsafe { tfhe_batch_bootstrap(self.raw, ctxt.p.as_ptr(), out.p.as_mut_ptr(), 1, 1) });
+        out
+    }
+    fn bootstrap_without_key_switch(&self, ctxt: &Ciphertext, cloud_key: &CloudKey) -> Ciphertext {
+        self.bind(cloud_key);
+        let mut out = Ciphertext::new();
+        check(unsafe { tfhe_batch_bootstrap(self.raw, ctxt.p.as_ptr(), out.p.as_mut_ptr(), 1, 0) });
+        out
+    }
+    fn name(&self) -> &str { "cuda-b200" }
+}
+
+// gates.rs:352-547 re-routed: `pub fn batch_nand(inputs, cloud_key)` becomes
+//   cuda::default_engine().batch_gate(Gate::Nand, inputs, cloud_key)
+pub fn default_engine() -> &'static CudaBootstrap {
+    static ENGINE: std::sync::OnceLock<CudaBootstrap> = std::sync::OnceLock::new();
+    ENGINE.get_or_init(|| CudaBootstrap::new(0))
+}
+#[allow(dead_code)]
+fn _unused(_: *mut c_void) {}
