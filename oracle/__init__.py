@@ -245,6 +245,35 @@ class Keys:
                                           C.byref(rng.s), _p(out[i]))
         return out
 
+    def encrypt_f64_batch(self, mu, seed: int):
+        """tlwe.rs:37-53 over a batch (OpenMP, one seeded stream per element)."""
+        mu = np.ascontiguousarray(mu, dtype=np.float64)
+        out = np.empty((mu.shape[0], self.params.n + 1), dtype=np.uint32)
+        lib().orc_lwe_encrypt_batch(C.byref(self._c), _p(mu), C.c_size_t(mu.shape[0]),
+                                    C.c_double(self.params.alpha_lv0), _p(self.s0),
+                                    C.c_uint64(seed), _p(out))
+        return out
+
+    def encrypt_bool_batch(self, bits, seed: int):
+        return self.encrypt_f64_batch(np.where(np.asarray(bits).astype(bool), 0.125, -0.125), seed)
+
+    def encrypt_message_batch(self, msgs, modulus: int, seed: int):
+        m = np.asarray(msgs) % modulus
+        return self.encrypt_f64_batch(m.astype(np.float64) * (1.0 / (2.0 * modulus)), seed)
+
+    def phase_batch(self, cts):
+        cts = np.ascontiguousarray(cts, dtype=np.uint32)
+        out = np.empty(cts.shape[0], dtype=np.uint32)
+        lib().orc_lwe_phase_batch(_p(cts), C.c_size_t(cts.shape[0]), _p(self.s0), self.params.n, _p(out))
+        return out
+
+    def decrypt_bool_batch(self, cts):
+        return self.phase_batch(cts).view(np.int32) >= 0
+
+    def decrypt_message_batch(self, cts, modulus: int):
+        f = self.phase_batch(cts).astype(np.float64) / 4294967296.0      # tlwe.rs:118-125
+        return (f / (1.0 / (2.0 * modulus)) + 0.5).astype(np.int64) % modulus
+
     def phase(self, cts, level: int = 0):
         cts = np.atleast_2d(_u32(cts))
         key = self.s0 if level == 0 else self.s1

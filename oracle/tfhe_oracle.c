@@ -293,6 +293,22 @@ uint32_t orc_lwe_decrypt_message(const uint32_t *ct, const uint32_t *key,
   return (uint32_t)(m % modulus);
 }
 
+void orc_lwe_encrypt_batch(const orc_params *p, const double *mu, size_t count, double alpha,
+                           const uint32_t *s0, uint64_t seed, uint32_t *cts) {
+  const size_t w = p->n + 1;
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < (long)count; i++) {
+    orc_rng r;
+    orc_rng_seed(&r, seed + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1));
+    orc_lwe_encrypt_f64(p, mu[i], alpha, s0, &r, cts + (size_t)i * w);
+  }
+}
+void orc_lwe_phase_batch(const uint32_t *cts, size_t count, const uint32_t *key, uint32_t n,
+                         uint32_t *phases) {
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < (long)count; i++) phases[i] = orc_lwe_phase(cts + (size_t)i * (n + 1), key, n);
+}
+
 /* key.rs:102-122.  One RNG stream per i so the result is thread-count free. */
 void orc_gen_ksk(const orc_params *p, const uint32_t *s0, const uint32_t *s1,
                  uint64_t seed, uint32_t *ksk) {

@@ -97,6 +97,12 @@ int orc_lwe_decrypt_bool(const uint32_t *ct, const uint32_t *key, uint32_t n);
 uint32_t orc_lwe_decrypt_message(const uint32_t *ct, const uint32_t *key,
                                  uint32_t n, uint32_t modulus);
 
+/* batch helpers for large trial counts (OpenMP; one RNG stream per element) */
+void orc_lwe_encrypt_batch(const orc_params *p, const double *mu, size_t count, double alpha,
+                           const uint32_t *s0, uint64_t seed, uint32_t *cts);
+void orc_lwe_phase_batch(const uint32_t *cts, size_t count, const uint32_t *key, uint32_t n,
+                         uint32_t *phases);
+
 /* ---- the hot path */
 /* gates.rs:54-150 (prep only).  op codes == enum tfhe_gate in include/tfhe_b200.h */
 void orc_gate_prep(const orc_params *p, int op, const uint32_t *a,

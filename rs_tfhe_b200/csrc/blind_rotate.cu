@@ -15,6 +15,7 @@
 // key crosses L2->SM once per CTA per step regardless of G.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "br_core.cuh"
 #include "kernels.h"
@@ -24,8 +25,8 @@ using namespace br;
 #ifndef BR_PRODUCER_SLEEP_NS
 #define BR_PRODUCER_SLEEP_NS 256
 #endif
-#ifndef BR_STAGGER_NS
-#define BR_STAGGER_NS 0
+#ifndef BR_DEFAULT_VARIANT
+#define BR_DEFAULT_VARIANT 1
 #endif
 
 namespace {
@@ -95,24 +96,70 @@ __constant__ uint32_t c_gate_off[TFHE_GATE_COUNT] = {0x20000000u, 0xE0000000u, 0
 
 constexpr int kStageBytes = kChunkCplx * 16;  // 16 KB: one BSK row
 
-template <int L> struct Cfg {
-  static constexpr int NBUF = L > 2 ? L : 2;
+// ---- TMEM as per-thread private scratch (pass-A twiddles) --------------------------
+// Warp w may touch TMEM lanes 32*(w%4)..+31; a 32x32b access gives every thread of the
+// warp its own lane, i.e. private storage with a data path separate from shared memory.
+__device__ __forceinline__ void tmem_st_ta(uint32_t taddr, const cplx (&ta)[8]) {
+  uint32_t r[32];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    r[4 * i + 0] = (uint32_t)__double2loint(ta[i].x); r[4 * i + 1] = (uint32_t)__double2hiint(ta[i].x);
+    r[4 * i + 2] = (uint32_t)__double2loint(ta[i].y); r[4 * i + 3] = (uint32_t)__double2hiint(ta[i].y);
+  }
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+      "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+      "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_ta(uint32_t taddr, cplx (&ta)[8]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    ta[i].x = __hiloint2double((int)r[4 * i + 1], (int)r[4 * i + 0]);
+    ta[i].y = __hiloint2double((int)r[4 * i + 3], (int)r[4 * i + 2]);
+  }
+}
+
+template <int L, int NBUF> struct Cfg {
   static constexpr int kAccBytes = 2 * kN * 4;
   static constexpr int kExchBytes = NBUF * kExchStride * 16;
   static constexpr int kAbarBytes = 2432;  // u16[n], n <= 1216
   static constexpr int kGroupBytes = kAccBytes + kExchBytes + kAbarBytes;
 };
 
-template <int L, int BGBIT, int G, int STAGES>
+// Kernel variants (same per-thread code, different residency):
+//   V1: G=4 groups, 3 exchange buffers, twiddles in registers   (consumers 232 regs)
+//   V2: G=6 groups, 2 exchange buffers (digits in sub-rounds of <=2), pass-A twiddles in
+//       TMEM, pass-B twiddles rebuilt from three base values     (consumers 160 regs)
+template <int L, int BGBIT, int G, int STAGES, int NBUF, bool TMEM_TW, int REGS_CONS, int REGS_PROD>
 __global__ void __launch_bounds__(G * 64 + 128, 1) blind_rotate_kernel(const BrArgs args) {
-  using C = Cfg<L>;
+  using C = Cfg<L, NBUF>;
   constexpr int L2 = 2 * L;
   constexpr bool EXACT = (L == 3 && BGBIT == 6);
+  static_assert(NBUF >= 2 && (L <= NBUF || (L == 3 && NBUF == 2)), "unsupported buffer plan");
+  constexpr int ND0 = L <= NBUF ? L : 2;   // digits in the first sub-round
+  constexpr int ND1 = L - ND0;             // and in the second (0 or 1)
   extern __shared__ __align__(128) uint8_t smem[];
   cplx *ring = reinterpret_cast<cplx *>(smem);
   uint8_t *groups = smem + STAGES * kStageBytes;
   uint64_t *full = reinterpret_cast<uint64_t *>(groups + G * C::kGroupBytes);
   uint64_t *empty = full + STAGES;
+  uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(empty + STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t n = args.n;
@@ -127,13 +174,20 @@ __global__ void __launch_bounds__(G * 64 + 128, 1) blind_rotate_kernel(const BrA
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (TMEM_TW && warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(
+        smem_u32(tmem_base_s)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (TMEM_TW) asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
+  if (TMEM_TW) asm volatile("tcgen05.fence::after_thread_sync;");
 
   // Register budget: the SM sub-partition hosting the producer warpgroup also hosts
-  // consumer warps, so the launch is compiled at 168 registers/thread and rebalanced
-  // here: the producer warpgroup shrinks to 40, the consumer warpgroups grow to 232.
+  // consumer warps, so the launch is compiled at 65536/blockDim registers/thread and
+  // rebalanced here (SASS: USETMAXREG).
   if (warp >= 2 * G) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PROD));
     // ===== producer: stream BSK rows (i, r) for every round =====
     if (warp == 2 * G && lane == 0) {
       const uint8_t *src0 = reinterpret_cast<const uint8_t *>(args.bsk);
@@ -153,7 +207,7 @@ __global__ void __launch_bounds__(G * 64 + 128, 1) blind_rotate_kernel(const BrA
   }
 
   // ===== consumers: group g owns one ciphertext per round =====
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_CONS));
   const int g = warp >> 1;
   const int tid = threadIdx.x & 63;
   uint8_t *gbase = groups + g * C::kGroupBytes;
@@ -161,11 +215,39 @@ __global__ void __launch_bounds__(G * 64 + 128, 1) blind_rotate_kernel(const BrA
   cplx *exch = reinterpret_cast<cplx *>(gbase + C::kAccBytes);
   uint16_t *abar_s = reinterpret_cast<uint16_t *>(gbase + C::kAccBytes + C::kExchBytes);
 
-  Twiddles tw;
+  // twiddles: V1 keeps both sets in registers; V2 parks ta in TMEM and keeps 3 tb bases
+  cplx ta_reg[TMEM_TW ? 1 : 8], tb_reg[TMEM_TW ? 1 : 8];
+  cplx tb1, tb2, tb4;
+  uint32_t taddr = 0;
+  {
+    const cplx *twb = args.tw_b + (tid & 7) * 8;
+    tb1 = twb[1]; tb2 = twb[2]; tb4 = twb[4];
+    if constexpr (TMEM_TW) {
+      cplx ta[8];
 #pragma unroll
-  for (int k = 0; k < 8; k++) {
-    tw.ta[k] = args.tw_a[tid * 8 + k];
-    tw.tb[k] = args.tw_b[(tid & 7) * 8 + k];
+      for (int k = 0; k < 8; k++) ta[k] = args.tw_a[tid * 8 + k];
+      taddr = *tmem_base_s + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * 32u;
+      tmem_st_ta(taddr, ta);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; k++) { ta_reg[k] = args.tw_a[tid * 8 + k]; tb_reg[k] = twb[k]; }
+    }
+  }
+#define BR_GET_TA(dst)                                   \
+  cplx dst[8];                                           \
+  if constexpr (TMEM_TW) tmem_ld_ta(taddr, dst);         \
+  else { _Pragma("unroll") for (int k_ = 0; k_ < 8; k_++) dst[k_] = ta_reg[k_]; }
+#define BR_GET_TB(dst)                                   \
+  cplx dst[8];                                           \
+  if constexpr (TMEM_TW) expand_tb(tb1, tb2, tb4, dst);  \
+  else { _Pragma("unroll") for (int k_ = 0; k_ < 8; k_++) dst[k_] = tb_reg[k_]; }
+#define BR_MAC_DIGITS(ND)                                                                   \
+  _Pragma("unroll") for (int d = 0; d < (ND); d++) {                                        \
+    mbar_wait(&full[stage], parity);                                                        \
+    fwd_pass_c_mac(tid, exch + d * kExchStride, ring + stage * kChunkCplx, racc);           \
+    __syncwarp();                                                                           \
+    if (lane == 0) mbar_arrive(&empty[stage]);                                              \
+    if (++stage == STAGES) { stage = 0; parity ^= 1; }                                      \
   }
 
   const uint32_t w = n + 1;
@@ -200,11 +282,10 @@ __global__ void __launch_bounds__(G * 64 + 128, 1) blind_rotate_kernel(const BrA
         acc[x] = rot_coeff(tv + (x & ~(kN - 1)), x & (kN - 1), b_tilda);
     }
     group_sync(g);
-    if (BR_STAGGER_NS > 0 && rd == 0) __nanosleep(g * BR_STAGGER_NS);
 
     for (uint32_t i = 0; i < n; i++) {
-      cplx racc[2][8];
       if (active) {
+        cplx racc[2][8];
         const uint32_t abar = abar_s[i];
 #pragma unroll
         for (int o = 0; o < 2; o++)
@@ -212,25 +293,46 @@ __global__ void __launch_bounds__(G * 64 + 128, 1) blind_rotate_kernel(const BrA
           for (int k = 0; k < 8; k++) racc[o][k] = mk(0.0, 0.0);
 #pragma unroll 1
         for (int p = 0; p < 2; p++) {
-          fwd_pass_a<L, BGBIT>(tid, acc + p * kN, abar, args.offset, tw, exch);
-          group_sync(g);
-          fwd_pass_b<L>(tid, tw, exch);
-          group_sync(g);
-#pragma unroll
-          for (int d = 0; d < L; d++) {
-            mbar_wait(&full[stage], parity);
-            fwd_pass_c_mac(tid, exch + d * kExchStride, ring + stage * kChunkCplx, racc);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[stage]);
-            if (++stage == STAGES) { stage = 0; parity ^= 1; }
+          uint32_t t_re[8], t_im[8];
+          load_t(tid, acc + p * kN, abar, args.offset, t_re, t_im);
+          {
+            BR_GET_TA(ta)
+            fwd_pass_a<BGBIT, 0, ND0>(tid, t_re, t_im, ta, exch);
           }
           group_sync(g);
+          {
+            BR_GET_TB(tb)
+            fwd_pass_b<ND0>(tid, tb, exch);
+          }
+          group_sync(g);
+          BR_MAC_DIGITS(ND0)
+          group_sync(g);
+          if constexpr (ND1 > 0) {
+            {
+              BR_GET_TA(ta)
+              fwd_pass_a<BGBIT, ND0, ND1>(tid, t_re, t_im, ta, exch);
+            }
+            group_sync(g);
+            {
+              BR_GET_TB(tb)
+              fwd_pass_b<ND1>(tid, tb, exch);
+            }
+            group_sync(g);
+            BR_MAC_DIGITS(ND1)
+            group_sync(g);
+          }
         }
-        inv_pass_c(tid, tw, racc, exch);
+        {
+          BR_GET_TB(tb)
+          inv_pass_c(tid, tb, racc, exch);
+        }
         group_sync(g);
         inv_pass_b(tid, exch);
         group_sync(g);
-        inv_pass_a<EXACT>(tid, tw, exch, acc);
+        {
+          BR_GET_TA(ta)
+          inv_pass_a<EXACT>(tid, ta, exch, acc);
+        }
         group_sync(g);
       } else {
         // idle group: keep the ring's phase accounting in lock step
@@ -262,24 +364,47 @@ __global__ void __launch_bounds__(G * 64 + 128, 1) blind_rotate_kernel(const BrA
     }
     group_sync(g);
   }
+#undef BR_GET_TA
+#undef BR_GET_TB
+#undef BR_MAC_DIGITS
+  if constexpr (TMEM_TW) {
+    asm volatile("bar.sync 15, %0;" ::"n"(G * 64) : "memory");  // all consumers done with TMEM
+    if (warp == 0)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(*tmem_base_s));
+  }
 }
 
-template <int L, int BGBIT>
-cudaError_t launch_t(const BrArgs &args, int num_sms, cudaStream_t stream) {
-  constexpr int G = 4, STAGES = 4;
-  auto kern = blind_rotate_kernel<L, BGBIT, G, STAGES>;
-  const int smem = STAGES * kStageBytes + G * Cfg<L>::kGroupBytes + 2 * STAGES * 8;
+template <int L, int BGBIT, int G, int STAGES, int NBUF, bool TMEM_TW, int RC, int RP>
+cudaError_t launch_v(const BrArgs &args, int num_sms, cudaStream_t stream) {
+  auto kern = blind_rotate_kernel<L, BGBIT, G, STAGES, NBUF, TMEM_TW, RC, RP>;
+  const int smem = STAGES * kStageBytes + G * Cfg<L, NBUF>::kGroupBytes + 2 * STAGES * 8 + 16;
   static bool configured = false;  // per instantiation
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  size_t groups = (args.count + G - 1) / G;
-  int grid = (int)(groups < (size_t)num_sms ? groups : (size_t)num_sms);
+  int grid = (int)(args.count < (size_t)num_sms ? args.count : (size_t)num_sms);
   if (grid < 1) grid = 1;
   kern<<<grid, G * 64 + 128, smem, stream>>>(args);
   return cudaGetLastError();
+}
+
+int br_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("TFHE_BR_VARIANT");
+    v = e ? atoi(e) : BR_DEFAULT_VARIANT;
+    if (v != 1 && v != 2) v = BR_DEFAULT_VARIANT;
+  }
+  return v;
+}
+
+template <int L, int BGBIT>
+cudaError_t launch_t(const BrArgs &args, int num_sms, cudaStream_t stream) {
+  if (br_variant() == 2)
+    return launch_v<L, BGBIT, 6, 3, 2, true, 160, 24>(args, num_sms, stream);
+  return launch_v<L, BGBIT, 4, 4, 3, false, 232, 40>(args, num_sms, stream);
 }
 
 }  // namespace

@@ -131,29 +131,42 @@ BR_HD uint32_t rot_coeff(const uint32_t *tv, int j, uint32_t k) {
   return (idx & 1024u) ? ~r : r;
 }
 
-// ---- per-thread state ---------------------------------------------------------
-struct Twiddles {
-  cplx ta[8];  // e^{i pi r (1-4 k0)/1024}, r = tid           (pass A / A')
-  cplx tb[8];  // e^{-2 pi i (tid&7) x/64}                     (pass B / C')
-};
+// ---- twiddles ------------------------------------------------------------------
+// ta[k0] = e^{i pi r (1-4 k0)/1024}, r = tid          (pass A post- / pass A' pre-twiddle)
+// tb[x]  = e^{-2 pi i (tid&7) x/64}                    (pass B post- / pass C' post-twiddle)
+// tb is a geometric sequence: it can be rebuilt from tb[1], tb[2], tb[4].
+BR_HD void expand_tb(cplx c1, cplx c2, cplx c4, cplx (&tb)[8]) {
+  tb[0] = mk(1.0, 0.0);
+  tb[1] = c1; tb[2] = c2; tb[4] = c4;
+  tb[3] = cmul(c1, c2);
+  tb[5] = cmul(c1, c4);
+  tb[6] = cmul(c2, c4);
+  tb[7] = cmul(tb[3], c4);
+}
 
 // ---- forward passes -------------------------------------------------------------
-// Pass A for all L digits of polynomial `accp` (decomposition trgsw.rs:144-171 fused
-// with the twist, klemsa.rs:96-103): thread tid owns complex points 64m+tid.
-template <int L, int BGBIT>
-BR_HD void fwd_pass_a(int tid, const uint32_t *accp, uint32_t abar, uint32_t offset,
-                      const Twiddles &tw, cplx *exch) {
-  constexpr uint32_t MASK = (1u << BGBIT) - 1u;
-  constexpr int HALFBG = 1 << (BGBIT - 1);
-  uint32_t t_re[8], t_im[8];
+// Rotate-subtract + decomposition offset for the 16 coefficients a thread owns
+// (trgsw.rs:212-215,183-186 fused with the `+ offset` of trgsw.rs:159-160).
+BR_HD void load_t(int tid, const uint32_t *accp, uint32_t abar, uint32_t offset,
+                  uint32_t (&t_re)[8], uint32_t (&t_im)[8]) {
 #pragma unroll
   for (int m = 0; m < 8; m++) {
     int j = 64 * m + tid;
     t_re[m] = rot_diff(accp, j, abar) + offset;
     t_im[m] = rot_diff(accp, j + kHalf, abar) + offset;
   }
+}
+
+// Pass A for digits [D0, D0+ND) of one polynomial (decomposition trgsw.rs:161-167 fused
+// with the twist, klemsa.rs:96-103): thread tid owns complex points 64m+tid; digit d goes
+// to exchange buffer d-D0.
+template <int BGBIT, int D0, int ND>
+BR_HD void fwd_pass_a(int tid, const uint32_t (&t_re)[8], const uint32_t (&t_im)[8],
+                      const cplx (&ta)[8], cplx *exch) {
+  constexpr uint32_t MASK = (1u << BGBIT) - 1u;
+  constexpr int HALFBG = 1 << (BGBIT - 1);
 #pragma unroll
-  for (int d = 0; d < L; d++) {
+  for (int d = D0; d < D0 + ND; d++) {
     const int sh = 32 - (d + 1) * BGBIT;
     cplx v[8];
 #define BR_LOAD(M)                                                              \
@@ -165,14 +178,14 @@ BR_HD void fwd_pass_a(int tid, const uint32_t *accp, uint32_t abar, uint32_t off
     BR_LOAD(0) BR_LOAD(1) BR_LOAD(2) BR_LOAD(3) BR_LOAD(4) BR_LOAD(5) BR_LOAD(6) BR_LOAD(7)
 #undef BR_LOAD
     dft8<false>(v);
-    cplx *e = exch + d * kExchStride + tid + (tid >> 3);
+    cplx *e = exch + (d - D0) * kExchStride + tid + (tid >> 3);
 #pragma unroll
-    for (int k0 = 0; k0 < 8; k0++) e[k0 * 72] = cmul(v[k0], tw.ta[k0]);
+    for (int k0 = 0; k0 < 8; k0++) e[k0 * 72] = cmul(v[k0], ta[k0]);
   }
 }
 
 // Pass B: thread u = (k0, j0) transforms over j1, twiddle e^{-2 pi i j0 k1/64}.
-template <int NB> BR_HD void fwd_pass_b(int tid, const Twiddles &tw, cplx *exch) {
+template <int NB> BR_HD void fwd_pass_b(int tid, const cplx (&tb)[8], cplx *exch) {
   const int k0 = tid >> 3, j0 = tid & 7;
 #pragma unroll
   for (int d = 0; d < NB; d++) {
@@ -183,7 +196,7 @@ template <int NB> BR_HD void fwd_pass_b(int tid, const Twiddles &tw, cplx *exch)
     dft8<false>(v);
     e[0] = v[0];
 #pragma unroll
-    for (int k1 = 1; k1 < 8; k1++) e[k1 * 9] = cmul(v[k1], tw.tb[k1]);
+    for (int k1 = 1; k1 < 8; k1++) e[k1 * 9] = cmul(v[k1], tb[k1]);
   }
 }
 
@@ -204,14 +217,14 @@ BR_HD void fwd_pass_c_mac(int tid, const cplx *exch_d, const cplx *bsk_row, cplx
 }
 
 // ---- inverse passes ---------------------------------------------------------------
-BR_HD void inv_pass_c(int tid, const Twiddles &tw, cplx (&acc)[2][8], cplx *exch) {
+BR_HD void inv_pass_c(int tid, const cplx (&tb)[8], cplx (&acc)[2][8], cplx *exch) {
 #pragma unroll
   for (int o = 0; o < 2; o++) {
     dft8<true>(acc[o]);
     cplx *e = exch + o * kExchStride + tid * 9;
     e[0] = acc[o][0];
 #pragma unroll
-    for (int j0 = 1; j0 < 8; j0++) e[j0] = cmulc(acc[o][j0], tw.tb[j0]);
+    for (int j0 = 1; j0 < 8; j0++) e[j0] = cmulc(acc[o][j0], tb[j0]);
   }
 }
 
@@ -232,13 +245,13 @@ BR_HD void inv_pass_b(int tid, cplx *exch) {
 // Pass A' + untwist + torus rounding (klemsa.rs:136-147) + accumulator update
 // (trgsw.rs:190-193).  acc points at this ciphertext's u32[2][1024].
 template <bool EXACT>
-BR_HD void inv_pass_a(int tid, const Twiddles &tw, const cplx *exch, uint32_t *acc) {
+BR_HD void inv_pass_a(int tid, const cplx (&ta)[8], const cplx *exch, uint32_t *acc) {
 #pragma unroll
   for (int o = 0; o < 2; o++) {
     const cplx *e = exch + o * kExchStride + tid + (tid >> 3);
     cplx v[8];
 #pragma unroll
-    for (int k0 = 0; k0 < 8; k0++) v[k0] = cmulc(e[k0 * 72], tw.ta[k0]);
+    for (int k0 = 0; k0 < 8; k0++) v[k0] = cmulc(e[k0 * 72], ta[k0]);
     dft8<true>(v);
     uint32_t *ap = acc + o * kN;
 #define BR_STORE(M)                                                       \
