@@ -26,7 +26,7 @@ using namespace br;
 #define BR_PRODUCER_SLEEP_NS 256
 #endif
 #ifndef BR_DEFAULT_VARIANT
-#define BR_DEFAULT_VARIANT 1
+#define BR_DEFAULT_VARIANT 3
 #endif
 
 namespace {
@@ -395,7 +395,7 @@ int br_variant() {
   if (v < 0) {
     const char *e = getenv("TFHE_BR_VARIANT");
     v = e ? atoi(e) : BR_DEFAULT_VARIANT;
-    if (v != 1 && v != 2) v = BR_DEFAULT_VARIANT;
+    if (v < 1 || v > 3) v = BR_DEFAULT_VARIANT;
   }
   return v;
 }
@@ -404,6 +404,8 @@ template <int L, int BGBIT>
 cudaError_t launch_t(const BrArgs &args, int num_sms, cudaStream_t stream) {
   if (br_variant() == 2)
     return launch_v<L, BGBIT, 6, 3, 2, true, 160, 24>(args, num_sms, stream);
+  if (br_variant() == 3)  // V1 residency, but twiddles out of the register file (more ILP room)
+    return launch_v<L, BGBIT, 4, 4, 3, true, 232, 40>(args, num_sms, stream);
   return launch_v<L, BGBIT, 4, 4, 3, false, 232, 40>(args, num_sms, stream);
 }
 
