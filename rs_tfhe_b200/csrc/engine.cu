@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -60,7 +61,8 @@ struct tfhe_engine {
   std::mutex mu;
   // cloud key: one contiguous device blob = BSK | KSK | test-vector slots
   uint8_t *blob = nullptr;
-  size_t blob_bytes = 0, off_ksk = 0, off_tv = 0;
+  size_t blob_bytes = 0, off_ksk = 0, off_kmma = 0, off_tv = 0;
+  bool has_kmma = false;  // basebit == 2: tensor-pipe key switch available
   bool key_loaded = false;
   uint32_t decomp_offset = 0;
   uint32_t ksk_rows = 0, ksk_stride = 0;
@@ -73,6 +75,7 @@ struct tfhe_engine {
 
   const cplx *bsk() const { return reinterpret_cast<const cplx *>(blob); }
   const uint32_t *ksk() const { return reinterpret_cast<const uint32_t *>(blob + off_ksk); }
+  const uint32_t *kmma() const { return reinterpret_cast<const uint32_t *>(blob + off_kmma); }
   uint32_t *tv() const { return reinterpret_cast<uint32_t *>(blob + off_tv); }
 };
 
@@ -86,8 +89,11 @@ void blob_layout(tfhe_engine *e) {
   e->ksk_stride = ks_stride(p.n);
   size_t bsk_bytes = (size_t)p.n * 2 * p.l * br::kChunkCplx * sizeof(cplx);
   size_t ksk_bytes = ((size_t)e->ksk_rows + 1) * e->ksk_stride * 4;
+  e->has_kmma = (p.basebit == 2);
+  size_t kmma_bytes = e->has_kmma ? ks_mma_words(p.n, p.iks_t) * 4 : 0;
   e->off_ksk = align_up(bsk_bytes, 256);
-  e->off_tv = align_up(e->off_ksk + ksk_bytes, 256);
+  e->off_kmma = align_up(e->off_ksk + ksk_bytes, 256);
+  e->off_tv = align_up(e->off_kmma + kmma_bytes, 256);
   e->blob_bytes = e->off_tv + (size_t)kMaxLut * 2 * TFHE_N * 4;
 }
 
@@ -95,6 +101,26 @@ int ensure_blob(tfhe_engine *e) {
   if (e->blob) return TFHE_OK;
   blob_layout(e);
   CU(cudaMalloc(reinterpret_cast<void **>(&e->blob), e->blob_bytes));
+  return TFHE_OK;
+}
+
+// K4 dispatch: tensor-pipe GEMM for the gate sets, row-walk kernels otherwise
+// (TFHE_KS_VARIANT=rows forces the row-walk kernels for A/B measurements).
+int key_switch(tfhe_engine *e, const uint32_t *d_ext, uint32_t *d_out, size_t count) {
+  static const bool rows_only = [] { const char *v = getenv("TFHE_KS_VARIANT"); return v && v[0] == 'r'; }();
+  if (e->has_kmma && !rows_only) {
+    KsMmaArgs k{};
+    k.w = e->kmma(); k.ext = d_ext; k.out = d_out;
+    k.n = e->p.n; k.iks_t = e->p.iks_t; k.nxg = ks_mma_nxg(e->p.n); k.count = count;
+    CU(ks_mma_launch(k, e->stream));
+  } else {
+    KsArgs k{};
+    k.ksk = e->ksk(); k.ext = d_ext; k.out = d_out;
+    k.n = e->p.n; k.basebit = e->p.basebit; k.iks_t = e->p.iks_t;
+    k.stride = e->ksk_stride; k.zero_row = e->ksk_rows; k.count = count;
+    CU(ks_launch(k, e->stream));
+  }
+  e->launches++;
   return TFHE_OK;
 }
 
@@ -124,12 +150,8 @@ int run_device(tfhe_engine *e, int op, const uint8_t *d_ops, int lut_id, const u
   e->launches++;
   CU(cudaEventRecord(e->ev[1], e->stream));
   if (out_kind == 0) {
-    KsArgs k{};
-    k.ksk = e->ksk(); k.ext = static_cast<const uint32_t *>(e->s_ext.p); k.out = d_out;
-    k.n = e->p.n; k.basebit = e->p.basebit; k.iks_t = e->p.iks_t;
-    k.stride = e->ksk_stride; k.zero_row = e->ksk_rows; k.count = count;
-    CU(ks_launch(k, e->stream));
-    e->launches++;
+    int rc = key_switch(e, static_cast<const uint32_t *>(e->s_ext.p), d_out, count);
+    if (rc != TFHE_OK) return rc;
   }
   CU(cudaEventRecord(e->ev[2], e->stream));
   return TFHE_OK;
@@ -309,6 +331,12 @@ int tfhe_engine_load_cloud_key(tfhe_engine *e, uint32_t decomposition_offset,
                          reinterpret_cast<uint32_t *>(e->blob + e->off_ksk), e->ksk_rows, p.n,
                          e->ksk_stride, e->stream));
   e->launches += 2;
+  if (e->has_kmma) {
+    CU(ksk_mma_relayout_launch(static_cast<const uint32_t *>(e->s_misc.p),
+                               reinterpret_cast<uint32_t *>(e->blob + e->off_kmma), p.n, p.iks_t,
+                               e->stream));
+    e->launches++;
+  }
   CU(cudaMemsetAsync(e->tv(), 0, (size_t)kMaxLut * 2 * TFHE_N * 4, e->stream));
   CU(cudaMemcpyAsync(e->tv(), testvec_a, TFHE_N * 4, cudaMemcpyHostToDevice, e->stream));
   CU(cudaMemcpyAsync(e->tv() + TFHE_N, testvec_b, TFHE_N * 4, cudaMemcpyHostToDevice, e->stream));
@@ -438,13 +466,10 @@ int tfhe_batch_extract_key_switch(tfhe_engine *e, const uint32_t *in_trlwe, uint
                        cudaMemcpyHostToDevice, e->stream));
     CU(extract_launch(static_cast<const uint32_t *>(e->s_in.p), static_cast<uint32_t *>(e->s_ext.p),
                       c, e->stream));
-    KsArgs k{};
-    k.ksk = e->ksk(); k.ext = static_cast<const uint32_t *>(e->s_ext.p);
-    k.out = static_cast<uint32_t *>(e->s_out.p);
-    k.n = e->p.n; k.basebit = e->p.basebit; k.iks_t = e->p.iks_t;
-    k.stride = e->ksk_stride; k.zero_row = e->ksk_rows; k.count = c;
-    CU(ks_launch(k, e->stream));
-    e->launches += 2;
+    int rc = key_switch(e, static_cast<const uint32_t *>(e->s_ext.p),
+                        static_cast<uint32_t *>(e->s_out.p), c);
+    if (rc != TFHE_OK) return rc;
+    e->launches += 1;
     CU(cudaMemcpyAsync(out + base * w, e->s_out.p, c * w * 4, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
   }
