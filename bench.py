@@ -189,7 +189,12 @@ def synthetic_cloud_key(T, P, seed: int):
     are used by tests/, smoke() and the cpu_baseline parity check."""
     r = np.random.default_rng(seed)
     ksk = r.integers(0, 2**32, (P.ksk_rows, P.n + 1), dtype=np.uint32)
-    bsk = r.standard_normal((P.n, 2 * P.l, 2, N)) * 2.0**35
+    # Fourier image (klemsa.rs:88-117: twist, 512-point FFT, x2) of uniform random torus rows,
+    # so the arithmetic stays in the exact-integer regime exactly as with a real key
+    x = r.integers(-2**31, 2**31, (P.n * 2 * P.l * 2, N)).astype(np.float64)
+    z = (x[:, :N // 2] + 1j * x[:, N // 2:]) * np.exp(1j * np.pi * np.arange(N // 2) / N)
+    F = np.fft.fft(z, axis=1) * 2.0
+    bsk = np.concatenate([F.real, F.imag], axis=1).reshape(P.n, 2 * P.l, 2, N)
     tv_a = np.zeros(N, dtype=np.uint32)
     tv_b = np.full(N, 0x20000000, dtype=np.uint32)
     offset = sum((1 << (P.bgbit - 1)) << (32 - (i + 1) * P.bgbit) for i in range(P.l)) & 0xFFFFFFFF

@@ -68,7 +68,15 @@ struct tfhe_engine {
   uint32_t ksk_rows = 0, ksk_stride = 0;
   int n_lut = 1;
   cplx *tw_a = nullptr, *tw_b = nullptr;
-  Scratch s_in, s_ext, s_out, s_ops, s_misc;
+  Scratch s_misc;
+  // two pipeline slots: H2D of chunk k+1 and D2H of chunk k-1 overlap the kernels of chunk k
+  struct Slot {
+    Scratch in, ext, out, ops;
+    cudaEvent_t h2d_done = nullptr, br_start = nullptr, br_end = nullptr, ks_end = nullptr,
+                d2h_done = nullptr;
+    bool busy = false;
+  } slot[2];
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float last_ms[2] = {0.f, 0.f};
   uint64_t launches = 0;
@@ -127,8 +135,8 @@ int key_switch(tfhe_engine *e, const uint32_t *d_ext, uint32_t *d_out, size_t co
 // One pass over <= kChunk ciphertexts already on the device.
 //   gate mode: op >= 0 or d_ops != NULL; plain mode: op < 0 and d_ops == NULL.
 //   out_kind: 0 key-switched LWE [n+1]; 1 extract_2 [n+1]; 2 TRLWE [2][N]
-int run_device(tfhe_engine *e, int op, const uint8_t *d_ops, int lut_id, const uint32_t *d_in,
-               uint32_t *d_out, size_t count, int out_kind) {
+int run_device(tfhe_engine *e, tfhe_engine::Slot &sl, int op, const uint8_t *d_ops, int lut_id,
+               const uint32_t *d_in, uint32_t *d_out, size_t count, int out_kind) {
   if (!e->key_loaded) return fail(TFHE_ERR_NO_KEY, "cloud key not loaded");
   if (lut_id >= e->n_lut) return fail(TFHE_ERR_INVALID, "unknown lut id %d", lut_id);
   BrArgs a{};
@@ -138,26 +146,40 @@ int run_device(tfhe_engine *e, int op, const uint8_t *d_ops, int lut_id, const u
   a.in = d_in; a.ops = d_ops; a.op = op;
   a.n = e->p.n; a.offset = e->decomp_offset; a.count = count;
   if (out_kind == 0) {
-    CU(e->s_ext.reserve(count * (TFHE_N + 1) * 4));
-    a.out = static_cast<uint32_t *>(e->s_ext.p);
+    CU(sl.ext.reserve(count * (TFHE_N + 1) * 4));
+    a.out = static_cast<uint32_t *>(sl.ext.p);
     a.out_mode = BR_OUT_EXTRACT;
   } else {
     a.out = d_out;
     a.out_mode = out_kind == 1 ? BR_OUT_EXTRACT2 : BR_OUT_TRLWE;
   }
-  CU(cudaEventRecord(e->ev[0], e->stream));
+  CU(cudaEventRecord(sl.br_start, e->stream));
   CU(br_launch(e->p.l, e->p.bgbit, a, e->num_sms, e->stream));
   e->launches++;
-  CU(cudaEventRecord(e->ev[1], e->stream));
+  CU(cudaEventRecord(sl.br_end, e->stream));
   if (out_kind == 0) {
-    int rc = key_switch(e, static_cast<const uint32_t *>(e->s_ext.p), d_out, count);
+    int rc = key_switch(e, static_cast<const uint32_t *>(sl.ext.p), d_out, count);
     if (rc != TFHE_OK) return rc;
   }
-  CU(cudaEventRecord(e->ev[2], e->stream));
+  CU(cudaEventRecord(sl.ks_end, e->stream));
   return TFHE_OK;
 }
 
-// Host-buffer driver: H2D -> kernels -> D2H in chunks of kChunk ciphertexts.
+// wait for a slot's D2H and add its kernel times to the running totals
+int retire_slot(tfhe_engine::Slot &sl, float &ms0, float &ms1) {
+  if (!sl.busy) return TFHE_OK;
+  CU(cudaEventSynchronize(sl.d2h_done));
+  float t0 = 0.f, t1 = 0.f;
+  CU(cudaEventElapsedTime(&t0, sl.br_start, sl.br_end));
+  CU(cudaEventElapsedTime(&t1, sl.br_end, sl.ks_end));
+  ms0 += t0; ms1 += t1;
+  sl.busy = false;
+  return TFHE_OK;
+}
+
+// Host-buffer driver: chunks of a few dozen persistent-grid rounds flow through a two-slot
+// pipeline (copy-in stream -> engine stream -> copy-out stream), so the host<->device copies of
+// neighbouring chunks overlap the kernels.
 int run_host(tfhe_engine *e, int op, const uint8_t *ops, int lut_id, const uint32_t *in,
              size_t in_words, uint32_t *out, size_t out_words, size_t count, int out_kind) {
   if (!e) return fail(TFHE_ERR_INVALID, "null engine");
@@ -165,30 +187,44 @@ int run_host(tfhe_engine *e, int op, const uint8_t *ops, int lut_id, const uint3
   if (!in || !out) return fail(TFHE_ERR_INVALID, "null buffer");
   std::lock_guard<std::mutex> lock(e->mu);
   CU(cudaSetDevice(e->dev));
+  if (!e->key_loaded) return fail(TFHE_ERR_NO_KEY, "cloud key not loaded");
   float ms0 = 0.f, ms1 = 0.f;
-  for (size_t base = 0; base < count; base += kChunk) {
-    size_t c = count - base < kChunk ? count - base : kChunk;
-    CU(e->s_in.reserve(c * in_words * 4));
-    CU(e->s_out.reserve(c * out_words * 4));
-    CU(cudaMemcpyAsync(e->s_in.p, in + base * in_words, c * in_words * 4, cudaMemcpyHostToDevice,
-                       e->stream));
+  const size_t chunk = (size_t)e->num_sms * 4 * 28;  // 28 rounds of the persistent grid
+  // order after whatever the caller queued on the engine stream
+  CU(cudaEventRecord(e->ev[3], e->stream));
+  CU(cudaStreamWaitEvent(e->copy_in, e->ev[3], 0));
+  int k = 0;
+  for (size_t base = 0; base < count; base += chunk, k++) {
+    const size_t c = count - base < chunk ? count - base : chunk;
+    tfhe_engine::Slot &sl = e->slot[k & 1];
+    int rc = retire_slot(sl, ms0, ms1);
+    if (rc != TFHE_OK) return rc;
+    CU(sl.in.reserve(c * in_words * 4));
+    CU(sl.out.reserve(c * out_words * 4));
+    CU(cudaMemcpyAsync(sl.in.p, in + base * in_words, c * in_words * 4, cudaMemcpyHostToDevice,
+                       e->copy_in));
     const uint8_t *d_ops = nullptr;
     if (ops) {
-      CU(e->s_ops.reserve(c));
-      CU(cudaMemcpyAsync(e->s_ops.p, ops + base, c, cudaMemcpyHostToDevice, e->stream));
-      d_ops = static_cast<const uint8_t *>(e->s_ops.p);
+      CU(sl.ops.reserve(c));
+      CU(cudaMemcpyAsync(sl.ops.p, ops + base, c, cudaMemcpyHostToDevice, e->copy_in));
+      d_ops = static_cast<const uint8_t *>(sl.ops.p);
     }
-    int rc = run_device(e, op, d_ops, lut_id, static_cast<const uint32_t *>(e->s_in.p),
-                        static_cast<uint32_t *>(e->s_out.p), c, out_kind);
+    CU(cudaEventRecord(sl.h2d_done, e->copy_in));
+    CU(cudaStreamWaitEvent(e->stream, sl.h2d_done, 0));
+    rc = run_device(e, sl, op, d_ops, lut_id, static_cast<const uint32_t *>(sl.in.p),
+                    static_cast<uint32_t *>(sl.out.p), c, out_kind);
     if (rc != TFHE_OK) return rc;
-    CU(cudaMemcpyAsync(out + base * out_words, e->s_out.p, c * out_words * 4,
-                       cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaStreamSynchronize(e->stream));
-    float t0 = 0.f, t1 = 0.f;
-    cudaEventElapsedTime(&t0, e->ev[0], e->ev[1]);
-    cudaEventElapsedTime(&t1, e->ev[1], e->ev[2]);
-    ms0 += t0; ms1 += t1;
+    CU(cudaStreamWaitEvent(e->copy_out, sl.ks_end, 0));
+    CU(cudaMemcpyAsync(out + base * out_words, sl.out.p, c * out_words * 4, cudaMemcpyDeviceToHost,
+                       e->copy_out));
+    CU(cudaEventRecord(sl.d2h_done, e->copy_out));
+    sl.busy = true;
   }
+  for (auto &sl : e->slot) {
+    int rc = retire_slot(sl, ms0, ms1);
+    if (rc != TFHE_OK) return rc;
+  }
+  CU(cudaStreamSynchronize(e->stream));
   e->last_ms[0] = ms0; e->last_ms[1] = ms1;
   return TFHE_OK;
 }
@@ -236,7 +272,12 @@ int tfhe_engine_create(const tfhe_params *params, int device_id, tfhe_engine **o
   e->num_sms = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
   e->stream = e->own_stream;
+  CU(cudaStreamCreateWithFlags(&e->copy_in, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&e->copy_out, cudaStreamNonBlocking));
   for (auto &ev : e->ev) CU(cudaEventCreate(&ev));
+  for (auto &sl : e->slot)
+    for (cudaEvent_t *pe : {&sl.h2d_done, &sl.br_start, &sl.br_end, &sl.ks_end, &sl.d2h_done})
+      CU(cudaEventCreate(pe));
   // twiddles (br_core.cuh): ta[r][k0] = e^{i pi r(1-4k0)/1024}, tb[j][x] = e^{-2 pi i jx/64}
   std::vector<cplx> ta(64 * 8), tb(8 * 8);
   for (int r = 0; r < 64; r++)
@@ -266,7 +307,14 @@ void tfhe_engine_destroy(tfhe_engine *e) {
   if (e->blob) cudaFree(e->blob);
   if (e->tw_a) cudaFree(e->tw_a);
   if (e->tw_b) cudaFree(e->tw_b);
-  e->s_in.release(); e->s_ext.release(); e->s_out.release(); e->s_ops.release(); e->s_misc.release();
+  e->s_misc.release();
+  for (auto &sl : e->slot) {
+    sl.in.release(); sl.ext.release(); sl.out.release(); sl.ops.release();
+    for (cudaEvent_t pe : {sl.h2d_done, sl.br_start, sl.br_end, sl.ks_end, sl.d2h_done})
+      if (pe) cudaEventDestroy(pe);
+  }
+  if (e->copy_in) cudaStreamDestroy(e->copy_in);
+  if (e->copy_out) cudaStreamDestroy(e->copy_out);
   for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   delete e;
@@ -459,18 +507,18 @@ int tfhe_batch_extract_key_switch(tfhe_engine *e, const uint32_t *in_trlwe, uint
   const size_t w = e->p.n + 1;
   for (size_t base = 0; base < count; base += kChunk) {
     size_t c = count - base < kChunk ? count - base : kChunk;
-    CU(e->s_in.reserve(c * 2 * TFHE_N * 4));
-    CU(e->s_ext.reserve(c * (TFHE_N + 1) * 4));
-    CU(e->s_out.reserve(c * w * 4));
-    CU(cudaMemcpyAsync(e->s_in.p, in_trlwe + base * 2 * TFHE_N, c * 2 * TFHE_N * 4,
+    tfhe_engine::Slot &sl = e->slot[0];
+    CU(sl.in.reserve(c * 2 * TFHE_N * 4));
+    CU(sl.ext.reserve(c * (TFHE_N + 1) * 4));
+    CU(sl.out.reserve(c * w * 4));
+    CU(cudaMemcpyAsync(sl.in.p, in_trlwe + base * 2 * TFHE_N, c * 2 * TFHE_N * 4,
                        cudaMemcpyHostToDevice, e->stream));
-    CU(extract_launch(static_cast<const uint32_t *>(e->s_in.p), static_cast<uint32_t *>(e->s_ext.p),
-                      c, e->stream));
-    int rc = key_switch(e, static_cast<const uint32_t *>(e->s_ext.p),
-                        static_cast<uint32_t *>(e->s_out.p), c);
+    CU(extract_launch(static_cast<const uint32_t *>(sl.in.p), static_cast<uint32_t *>(sl.ext.p), c,
+                      e->stream));
+    int rc = key_switch(e, static_cast<const uint32_t *>(sl.ext.p), static_cast<uint32_t *>(sl.out.p), c);
     if (rc != TFHE_OK) return rc;
     e->launches += 1;
-    CU(cudaMemcpyAsync(out + base * w, e->s_out.p, c * w * 4, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(out + base * w, sl.out.p, c * w * 4, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
   }
   return TFHE_OK;
@@ -487,7 +535,7 @@ int tfhe_batch_gate_dev(tfhe_engine *e, tfhe_gate op, const uint8_t *d_ops,
   const size_t w = e->p.n + 1;
   for (size_t base = 0; base < count; base += kChunk) {
     size_t c = count - base < kChunk ? count - base : kChunk;
-    int rc = run_device(e, d_ops ? 0 : (int)op, d_ops ? d_ops + base : nullptr, -1,
+    int rc = run_device(e, e->slot[0], d_ops ? 0 : (int)op, d_ops ? d_ops + base : nullptr, -1,
                         d_in_pairs + base * 2 * w, d_out + base * w, c, 0);
     if (rc != TFHE_OK) return rc;
   }
@@ -503,7 +551,7 @@ int tfhe_batch_bootstrap_dev(tfhe_engine *e, int lut_id, const uint32_t *d_in, u
   const size_t w = e->p.n + 1;
   for (size_t base = 0; base < count; base += kChunk) {
     size_t c = count - base < kChunk ? count - base : kChunk;
-    int rc = run_device(e, -1, nullptr, lut_id, d_in + base * w, d_out + base * w, c,
+    int rc = run_device(e, e->slot[0], -1, nullptr, lut_id, d_in + base * w, d_out + base * w, c,
                         key_switch ? 0 : 1);
     if (rc != TFHE_OK) return rc;
   }
@@ -515,8 +563,8 @@ int tfhe_engine_synchronize(tfhe_engine *e) {
   CU(cudaSetDevice(e->dev));
   CU(cudaStreamSynchronize(e->stream));
   float t0 = 0.f, t1 = 0.f;
-  if (cudaEventElapsedTime(&t0, e->ev[0], e->ev[1]) == cudaSuccess &&
-      cudaEventElapsedTime(&t1, e->ev[1], e->ev[2]) == cudaSuccess) {
+  if (cudaEventElapsedTime(&t0, e->slot[0].br_start, e->slot[0].br_end) == cudaSuccess &&
+      cudaEventElapsedTime(&t1, e->slot[0].br_end, e->slot[0].ks_end) == cudaSuccess) {
     e->last_ms[0] = t0; e->last_ms[1] = t1;
   } else {
     cudaGetLastError();

@@ -11,7 +11,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu.json 2>> gpurun_out/bench.err
 ncu --set full --clock-control none --import-source on -k regex:blind_rotate -s 1 -c 1 -o gpurun_out/prof_br -f \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2>> gpurun_out/bench.err
-ncu --set full --clock-control none --import-source on -k regex:keyswitch -s 1 -c 1 -o gpurun_out/prof_ks -f \
+ncu --set full --clock-control none --import-source on -k regex:ks_mma -s 1 -c 1 -o gpurun_out/prof_ks -f \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2>> gpurun_out/bench.err
 tail -5 gpurun_out/bench.err
 ls -la gpurun_out
