@@ -117,7 +117,9 @@ def cpu_leg(params: str, sample: int, threads: int = 0, engine=None):
     the oracle's (real) key and compared word for word -- the oracle acting as checker."""
     import oracle as O
 
-    cores = O.max_threads() if threads <= 0 else threads
+    if threads <= 0:
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else O.max_threads()
+    cores = threads
     K = O.Keys(params, seed=0x5EED0001)
     if sample <= 0:
         sample = cores * 4
@@ -152,7 +154,8 @@ def run_reference_arm(args):
     if rank != 0:
         return
     import oracle as O
-    cores = O.max_threads()
+    # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     K = O.Keys(args.params, seed=0x5EED0001)
     sample = args.cpu_sample or cores * 8
     r = np.random.default_rng(7)
