@@ -146,10 +146,27 @@ int tfhe_lut_register(tfhe_engine *e, const uint32_t *poly_a /*[N] or NULL => 0*
  * bootstrap_func (lut.rs:49-65) = tfhe_lut_generate + this. */
 int tfhe_batch_bootstrap_lut(tfhe_engine *e, int lut_id, const uint32_t *in /*[count][n+1]*/,
                              uint32_t *out /*[count][n+1]*/, size_t count);
+/* Same with a per-ciphertext table (lut_ids[count]): independent LUT bootstraps of one circuit
+ * level -- e.g. the sum and carry tables of examples/lut_add_two_numbers.rs:138,147, which read
+ * the same input -- go out as ONE batch instead of one call per table. */
+int tfhe_batch_bootstrap_lut_multi(tfhe_engine *e, const int32_t *lut_ids /*[count]*/,
+                                   const uint32_t *in /*[count][n+1]*/, uint32_t *out, size_t count);
 /* Replaces: trgsw::identity_key_switching after trlwe::sample_extract_index(.,0)
  * (trgsw.rs:332-360, trlwe.rs:106-120) on caller-supplied TRLWE samples. */
 int tfhe_batch_extract_key_switch(tfhe_engine *e, const uint32_t *in_trlwe /*[count][2][N]*/,
                                   uint32_t *out /*[count][n+1]*/, size_t count);
+
+/* ---- next to the path: LWE proxy re-encryption = the key-switch kernel with the
+ *      level-0 dimension as input ------------------------------------------------------ */
+typedef struct tfhe_reenc_key tfhe_reenc_key;
+/* Replaces: holding a proxy_reenc::ProxyReencryptionKey (src/proxy_reenc.rs:224-233):
+ * key_encryptions u32[base*t*n][n+1], index base*t*i + base*j + k (proxy_reenc.rs:316,381). */
+int tfhe_reenc_key_load(tfhe_engine *e, const uint32_t *key_encryptions, uint32_t base, uint32_t t,
+                        tfhe_reenc_key **out);
+void tfhe_reenc_key_destroy(tfhe_reenc_key *k);
+/* Replaces: proxy_reenc::reencrypt_tlwe_lv0 (src/proxy_reenc.rs:468-511) over a batch. */
+int tfhe_batch_reencrypt(tfhe_engine *e, const tfhe_reenc_key *key, const uint32_t *in /*[count][n+1]*/,
+                         uint32_t *out /*[count][n+1]*/, size_t count);
 
 /* ---- the hot path, device-resident buffers (no copies; asynchronous on the
  *      engine stream).  Pointers are CUDA device pointers on the engine's GPU. */

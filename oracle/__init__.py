@@ -371,6 +371,27 @@ class Keys:
         return out
 
 
+def gen_reenc_key(K_from: "Keys", K_to: "Keys", seed: int, basebit: int = None, t: int = None):
+    """ProxyReencryptionKey::new_symmetric (src/proxy_reenc.rs:336-392)."""
+    p = K_from.params
+    basebit = p.basebit if basebit is None else basebit
+    t = p.iks_t if t is None else t
+    out = np.empty(((1 << basebit) * t * p.n, p.n + 1), dtype=np.uint32)
+    lib().orc_gen_reenc_key(C.byref(K_from._c), _p(K_from.s0), _p(K_to.s0), C.c_uint64(seed),
+                            C.c_uint32(basebit), C.c_uint32(t), _p(out))
+    return out
+
+
+def reencrypt(params: Params, reenc_key, basebit: int, t: int, ct):
+    """proxy_reenc::reencrypt_tlwe_lv0 (src/proxy_reenc.rs:468-511)."""
+    ct = _u32(ct)
+    key = _u32(reenc_key)
+    out = np.empty(params.n + 1, dtype=np.uint32)
+    c = params.c()
+    lib().orc_reencrypt(C.byref(c), _p(key), C.c_uint32(basebit), C.c_uint32(t), _p(ct), _p(out))
+    return out
+
+
 def max_threads() -> int:
     return lib().orc_max_threads()
 

@@ -546,6 +546,45 @@ void orc_bootstrap(const orc_params *p, uint32_t offset, const double *bsk_fft,
   }
 }
 
+/* ------------------------------------------------------- proxy re-encryption */
+
+/* proxy_reenc.rs:354-392 (new_symmetric_with_params) */
+void orc_gen_reenc_key(const orc_params *p, const uint32_t *key_from, const uint32_t *key_to,
+                       uint64_t seed, uint32_t basebit, uint32_t t, uint32_t *out) {
+  const uint32_t base = 1u << basebit, n = p->n, w = n + 1;
+  memset(out, 0, (size_t)base * t * n * w * sizeof(uint32_t));
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < (int)n; i++) {
+    orc_rng r;
+    orc_rng_seed(&r, seed ^ (0x52454E00ull + (uint64_t)i * 0x9E3779B97F4A7C15ull));
+    for (uint32_t j = 0; j < t; j++)
+      for (uint32_t k = 1; k < base; k++) {
+        double mu = (double)(k * key_from[i]) / (double)((uint64_t)1 << ((j + 1) * basebit));
+        size_t idx = ((size_t)base * t * i) + (size_t)base * j + k;
+        orc_lwe_encrypt_f64(p, mu, p->alpha_lv0, key_to, &r, out + idx * w);
+      }
+  }
+}
+
+/* proxy_reenc.rs:468-511 */
+void orc_reencrypt(const orc_params *p, const uint32_t *reenc_key, uint32_t basebit, uint32_t t,
+                   const uint32_t *ct_from, uint32_t *out) {
+  const uint32_t n = p->n, w = n + 1, base = 1u << basebit;
+  const uint32_t prec = 1u << (32 - (1 + basebit * t));
+  memset(out, 0, w * sizeof(uint32_t));
+  out[n] = ct_from[n];
+  for (uint32_t i = 0; i < n; i++) {
+    uint32_t a_bar = ct_from[i] + prec;
+    for (uint32_t j = 0; j < t; j++) {
+      uint32_t k = (a_bar >> (32 - (j + 1) * basebit)) & (base - 1);
+      if (k != 0) {
+        const uint32_t *rowp = reenc_key + ((size_t)base * t * i + (size_t)base * j + k) * w;
+        for (uint32_t x = 0; x < w; x++) out[x] -= rowp[x];
+      }
+    }
+  }
+}
+
 /* --------------------------------------------------------------------- LUT */
 
 /* lut/generator.rs:264-266 */

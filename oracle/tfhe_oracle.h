@@ -138,6 +138,12 @@ void orc_bootstrap(const orc_params *p, uint32_t offset, const double *bsk_fft,
                    const uint32_t *ksk, const uint32_t *tv_a, const uint32_t *tv_b,
                    const uint32_t *lwe, int key_switch, uint32_t *out);
 
+/* ---- proxy re-encryption (src/proxy_reenc.rs:354-392 symmetric key, :468-511 reencrypt) */
+void orc_gen_reenc_key(const orc_params *p, const uint32_t *key_from, const uint32_t *key_to,
+                       uint64_t seed, uint32_t basebit, uint32_t t, uint32_t *out /*[2^basebit*t*n][n+1]*/);
+void orc_reencrypt(const orc_params *p, const uint32_t *reenc_key, uint32_t basebit, uint32_t t,
+                   const uint32_t *ct_from, uint32_t *out);
+
 /* ---- LUT (lut/generator.rs:89-137,264-266; lut/encoder.rs:29-42,66-73) */
 uint32_t orc_div_round(uint32_t a, uint32_t b);
 uint32_t orc_lut_encode(uint32_t msg, uint32_t modulus, double scale);

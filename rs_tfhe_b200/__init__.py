@@ -144,9 +144,14 @@ def _load():
     L.tfhe_lut_register.argtypes = [vp, u32p, u32p, C.POINTER(C.c_int)]
     L.tfhe_batch_bootstrap_lut.argtypes = [vp, C.c_int, u32p, u32p, C.c_size_t]
     L.tfhe_batch_extract_key_switch.argtypes = [vp, u32p, u32p, C.c_size_t]
+    L.tfhe_batch_bootstrap_lut_multi.argtypes = [vp, vp, u32p, u32p, C.c_size_t]
     L.tfhe_batch_gate_dev.argtypes = [vp, C.c_int, vp, vp, vp, C.c_size_t]
     L.tfhe_batch_bootstrap_dev.argtypes = [vp, C.c_int, vp, vp, C.c_size_t, C.c_int]
     L.tfhe_engine_synchronize.argtypes = [vp]
+    L.tfhe_reenc_key_load.argtypes = [vp, u32p, C.c_uint32, C.c_uint32, C.POINTER(vp)]
+    L.tfhe_reenc_key_destroy.argtypes = [vp]
+    L.tfhe_reenc_key_destroy.restype = None
+    L.tfhe_batch_reencrypt.argtypes = [vp, vp, u32p, u32p, C.c_size_t]
     L.tfhe_probe_fp64_tflops.argtypes = [vp, C.POINTER(C.c_double)]
     if L.tfhe_abi_version() != 1:
         raise EngineError("libtfhe_b200.so ABI version mismatch")
@@ -345,14 +350,43 @@ class CudaBootstrap:
         _check(_load().tfhe_lut_register(self._h, _ptr(a), _ptr(_u32(poly_b, (N,))), C.byref(lut_id)))
         return lut_id.value
 
-    def batch_bootstrap_lut(self, lut_id: int, ctxt, cloud_key: Optional[CloudKey] = None):
+    def batch_bootstrap_lut(self, lut_id, ctxt, cloud_key: Optional[CloudKey] = None):
+        """LutBootstrap::bootstrap_lut over a batch; `lut_id` may be one id or one id per
+        ciphertext (independent tables of one circuit level in a single batch)."""
         self._bind(cloud_key)
         w = self.params.n + 1
         cts = _u32(ctxt, (w,))
         single = cts.ndim == 1
         cts = cts.reshape(-1, w)
         out = np.empty_like(cts)
-        _check(_load().tfhe_batch_bootstrap_lut(self._h, lut_id, _ptr(cts), _ptr(out), cts.shape[0]))
+        if np.ndim(lut_id) == 0:
+            _check(_load().tfhe_batch_bootstrap_lut(self._h, int(lut_id), _ptr(cts), _ptr(out), cts.shape[0]))
+        else:
+            ids = np.ascontiguousarray(lut_id, dtype=np.int32)
+            if ids.shape != (cts.shape[0],):
+                raise ValueError("need one lut id per ciphertext")
+            _check(_load().tfhe_batch_bootstrap_lut_multi(self._h, _ptr(ids), _ptr(cts), _ptr(out), cts.shape[0]))
+        return out[0] if single else out
+
+    # ---- proxy re-encryption (src/proxy_reenc.rs), SURVEY 8(f3)
+    def load_reenc_key(self, key_encryptions, base: int, t: int) -> "ReencKey":
+        """Upload a proxy_reenc::ProxyReencryptionKey{key_encryptions, base, t} (:224-233)."""
+        p = self.params
+        k = _u32(key_encryptions, (p.n + 1,)).reshape(-1, p.n + 1)
+        if k.shape[0] != base * t * p.n:
+            raise ValueError("key_encryptions must have base*t*n rows")
+        h = C.c_void_p()
+        _check(_load().tfhe_reenc_key_load(self._h, _ptr(k), base, t, C.byref(h)))
+        return ReencKey(h, base, t)
+
+    def batch_reencrypt(self, key: "ReencKey", cts) -> np.ndarray:
+        """proxy_reenc::reencrypt_tlwe_lv0 (src/proxy_reenc.rs:468-511) over a batch."""
+        w = self.params.n + 1
+        c = _u32(cts, (w,))
+        single = c.ndim == 1
+        c = c.reshape(-1, w)
+        out = np.empty_like(c)
+        _check(_load().tfhe_batch_reencrypt(self._h, key._h, _ptr(c), _ptr(out), c.shape[0]))
         return out[0] if single else out
 
     # ---- device-resident (raw CUDA pointers; asynchronous on the engine stream)
@@ -365,6 +399,24 @@ class CudaBootstrap:
                             key_switch: bool = True) -> None:
         _check(_load().tfhe_batch_bootstrap_dev(self._h, lut_id, C.c_void_p(d_in), C.c_void_p(d_out),
                                                 count, int(key_switch)))
+
+
+class ReencKey:
+    """Device-resident proxy re-encryption key."""
+
+    def __init__(self, handle, base: int, t: int):
+        self._h, self.base, self.t = handle, base, t
+
+    def close(self) -> None:
+        if self._h and self._h.value:
+            _load().tfhe_reenc_key_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 _default: dict = {}

@@ -71,7 +71,7 @@ struct tfhe_engine {
   Scratch s_misc;
   // two pipeline slots: H2D of chunk k+1 and D2H of chunk k-1 overlap the kernels of chunk k
   struct Slot {
-    Scratch in, ext, out, ops;
+    Scratch in, ext, out, ops, idx;
     cudaEvent_t h2d_done = nullptr, br_start = nullptr, br_end = nullptr, ks_end = nullptr,
                 d2h_done = nullptr;
     bool busy = false;
@@ -85,6 +85,13 @@ struct tfhe_engine {
   const uint32_t *ksk() const { return reinterpret_cast<const uint32_t *>(blob + off_ksk); }
   const uint32_t *kmma() const { return reinterpret_cast<const uint32_t *>(blob + off_kmma); }
   uint32_t *tv() const { return reinterpret_cast<uint32_t *>(blob + off_tv); }
+};
+
+// proxy_reenc::ProxyReencryptionKey (src/proxy_reenc.rs:224-233) resident on the device
+struct tfhe_reenc_key {
+  uint32_t *rows = nullptr;  // [base*t*n + 1][stride], last row zero
+  uint32_t basebit = 0, t = 0, n_rows = 0;
+  int dev = 0;
 };
 
 namespace {
@@ -125,7 +132,7 @@ int key_switch(tfhe_engine *e, const uint32_t *d_ext, uint32_t *d_out, size_t co
     KsArgs k{};
     k.ksk = e->ksk(); k.ext = d_ext; k.out = d_out;
     k.n = e->p.n; k.basebit = e->p.basebit; k.iks_t = e->p.iks_t;
-    k.stride = e->ksk_stride; k.zero_row = e->ksk_rows; k.count = count;
+    k.stride = e->ksk_stride; k.zero_row = e->ksk_rows; k.n_in = TFHE_N; k.count = count;
     CU(ks_launch(k, e->stream));
   }
   e->launches++;
@@ -136,13 +143,14 @@ int key_switch(tfhe_engine *e, const uint32_t *d_ext, uint32_t *d_out, size_t co
 //   gate mode: op >= 0 or d_ops != NULL; plain mode: op < 0 and d_ops == NULL.
 //   out_kind: 0 key-switched LWE [n+1]; 1 extract_2 [n+1]; 2 TRLWE [2][N]
 int run_device(tfhe_engine *e, tfhe_engine::Slot &sl, int op, const uint8_t *d_ops, int lut_id,
-               const uint32_t *d_in, uint32_t *d_out, size_t count, int out_kind) {
+               const uint32_t *d_in, uint32_t *d_out, size_t count, int out_kind,
+               const int32_t *d_lut_ids = nullptr) {
   if (!e->key_loaded) return fail(TFHE_ERR_NO_KEY, "cloud key not loaded");
   if (lut_id >= e->n_lut) return fail(TFHE_ERR_INVALID, "unknown lut id %d", lut_id);
   BrArgs a{};
   a.bsk = e->bsk();
   a.tw_a = e->tw_a; a.tw_b = e->tw_b;
-  a.tv = e->tv(); a.tv_index = nullptr; a.tv_default = lut_id < 0 ? 0 : lut_id;
+  a.tv = e->tv(); a.tv_index = d_lut_ids; a.tv_default = lut_id < 0 ? 0 : lut_id;
   a.in = d_in; a.ops = d_ops; a.op = op;
   a.n = e->p.n; a.offset = e->decomp_offset; a.count = count;
   if (out_kind == 0) {
@@ -181,7 +189,8 @@ int retire_slot(tfhe_engine::Slot &sl, float &ms0, float &ms1) {
 // pipeline (copy-in stream -> engine stream -> copy-out stream), so the host<->device copies of
 // neighbouring chunks overlap the kernels.
 int run_host(tfhe_engine *e, int op, const uint8_t *ops, int lut_id, const uint32_t *in,
-             size_t in_words, uint32_t *out, size_t out_words, size_t count, int out_kind) {
+             size_t in_words, uint32_t *out, size_t out_words, size_t count, int out_kind,
+             const int32_t *lut_ids = nullptr) {
   if (!e) return fail(TFHE_ERR_INVALID, "null engine");
   if (count == 0) return TFHE_OK;
   if (!in || !out) return fail(TFHE_ERR_INVALID, "null buffer");
@@ -209,10 +218,16 @@ int run_host(tfhe_engine *e, int op, const uint8_t *ops, int lut_id, const uint3
       CU(cudaMemcpyAsync(sl.ops.p, ops + base, c, cudaMemcpyHostToDevice, e->copy_in));
       d_ops = static_cast<const uint8_t *>(sl.ops.p);
     }
+    const int32_t *d_ids = nullptr;
+    if (lut_ids) {
+      CU(sl.idx.reserve(c * 4));
+      CU(cudaMemcpyAsync(sl.idx.p, lut_ids + base, c * 4, cudaMemcpyHostToDevice, e->copy_in));
+      d_ids = static_cast<const int32_t *>(sl.idx.p);
+    }
     CU(cudaEventRecord(sl.h2d_done, e->copy_in));
     CU(cudaStreamWaitEvent(e->stream, sl.h2d_done, 0));
     rc = run_device(e, sl, op, d_ops, lut_id, static_cast<const uint32_t *>(sl.in.p),
-                    static_cast<uint32_t *>(sl.out.p), c, out_kind);
+                    static_cast<uint32_t *>(sl.out.p), c, out_kind, d_ids);
     if (rc != TFHE_OK) return rc;
     CU(cudaStreamWaitEvent(e->copy_out, sl.ks_end, 0));
     CU(cudaMemcpyAsync(out + base * out_words, sl.out.p, c * out_words * 4, cudaMemcpyDeviceToHost,
@@ -309,7 +324,7 @@ void tfhe_engine_destroy(tfhe_engine *e) {
   if (e->tw_b) cudaFree(e->tw_b);
   e->s_misc.release();
   for (auto &sl : e->slot) {
-    sl.in.release(); sl.ext.release(); sl.out.release(); sl.ops.release();
+    sl.in.release(); sl.ext.release(); sl.out.release(); sl.ops.release(); sl.idx.release();
     for (cudaEvent_t pe : {sl.h2d_done, sl.br_start, sl.br_end, sl.ks_end, sl.d2h_done})
       if (pe) cudaEventDestroy(pe);
   }
@@ -496,6 +511,17 @@ int tfhe_batch_bootstrap_lut(tfhe_engine *e, int lut_id, const uint32_t *in, uin
   return run_host(e, -1, nullptr, lut_id, in, w, out, w, count, 0);
 }
 
+int tfhe_batch_bootstrap_lut_multi(tfhe_engine *e, const int32_t *lut_ids, const uint32_t *in,
+                                   uint32_t *out, size_t count) {
+  if (!e) return fail(TFHE_ERR_INVALID, "null engine");
+  if (!lut_ids && count) return fail(TFHE_ERR_INVALID, "null lut_ids");
+  for (size_t i = 0; i < count; i++)
+    if (lut_ids[i] < 0 || lut_ids[i] >= e->n_lut)
+      return fail(TFHE_ERR_INVALID, "unknown lut id %d at %zu", lut_ids[i], i);
+  const size_t w = e->p.n + 1;
+  return run_host(e, -1, nullptr, 0, in, w, out, w, count, 0, lut_ids);
+}
+
 int tfhe_batch_extract_key_switch(tfhe_engine *e, const uint32_t *in_trlwe, uint32_t *out,
                                   size_t count) {
   if (!e) return fail(TFHE_ERR_INVALID, "null engine");
@@ -518,6 +544,69 @@ int tfhe_batch_extract_key_switch(tfhe_engine *e, const uint32_t *in_trlwe, uint
     int rc = key_switch(e, static_cast<const uint32_t *>(sl.ext.p), static_cast<uint32_t *>(sl.out.p), c);
     if (rc != TFHE_OK) return rc;
     e->launches += 1;
+    CU(cudaMemcpyAsync(out + base * w, sl.out.p, c * w * 4, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+  }
+  return TFHE_OK;
+}
+
+int tfhe_reenc_key_load(tfhe_engine *e, const uint32_t *key_encryptions, uint32_t base, uint32_t t,
+                        tfhe_reenc_key **out) {
+  if (!e || !key_encryptions || !out) return fail(TFHE_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (base < 2 || (base & (base - 1)) != 0) return fail(TFHE_ERR_INVALID, "base must be a power of two");
+  uint32_t basebit = 0;
+  while ((1u << basebit) < base) basebit++;
+  if (t == 0 || basebit * t > 31) return fail(TFHE_ERR_INVALID, "bad decomposition (basebit*t > 31)");
+  if ((size_t)8 * e->p.n * 4 > 48 * 1024) return fail(TFHE_ERR_INVALID, "n too large");
+  std::lock_guard<std::mutex> lock(e->mu);
+  CU(cudaSetDevice(e->dev));
+  tfhe_reenc_key *k = new (std::nothrow) tfhe_reenc_key();
+  if (!k) return fail(TFHE_ERR_ALLOC, "out of host memory");
+  k->basebit = basebit; k->t = t; k->n_rows = base * t * e->p.n; k->dev = e->dev;
+  const size_t src_bytes = (size_t)k->n_rows * (e->p.n + 1) * 4;
+  const size_t dst_bytes = ((size_t)k->n_rows + 1) * e->ksk_stride * 4;
+  CU(cudaMalloc(reinterpret_cast<void **>(&k->rows), dst_bytes));
+  CU(e->s_misc.reserve(src_bytes));
+  CU(cudaMemcpyAsync(e->s_misc.p, key_encryptions, src_bytes, cudaMemcpyHostToDevice, e->stream));
+  CU(ksk_relayout_launch(static_cast<const uint32_t *>(e->s_misc.p), k->rows, k->n_rows, e->p.n,
+                         e->ksk_stride, e->stream));
+  e->launches++;
+  CU(cudaStreamSynchronize(e->stream));
+  e->s_misc.release();
+  *out = k;
+  return TFHE_OK;
+}
+
+void tfhe_reenc_key_destroy(tfhe_reenc_key *k) {
+  if (!k) return;
+  cudaSetDevice(k->dev);
+  if (k->rows) cudaFree(k->rows);
+  delete k;
+}
+
+int tfhe_batch_reencrypt(tfhe_engine *e, const tfhe_reenc_key *key, const uint32_t *in, uint32_t *out,
+                         size_t count) {
+  if (!e || !key) return fail(TFHE_ERR_INVALID, "null argument");
+  if (count == 0) return TFHE_OK;
+  if (!in || !out) return fail(TFHE_ERR_INVALID, "null buffer");
+  if (key->dev != e->dev) return fail(TFHE_ERR_INVALID, "key lives on another device");
+  std::lock_guard<std::mutex> lock(e->mu);
+  CU(cudaSetDevice(e->dev));
+  const size_t w = e->p.n + 1;
+  for (size_t base = 0; base < count; base += kChunk) {
+    size_t c = count - base < kChunk ? count - base : kChunk;
+    tfhe_engine::Slot &sl = e->slot[0];
+    CU(sl.in.reserve(c * w * 4));
+    CU(sl.out.reserve(c * w * 4));
+    CU(cudaMemcpyAsync(sl.in.p, in + base * w, c * w * 4, cudaMemcpyHostToDevice, e->stream));
+    KsArgs k{};
+    k.ksk = key->rows; k.ext = static_cast<const uint32_t *>(sl.in.p);
+    k.out = static_cast<uint32_t *>(sl.out.p);
+    k.n = e->p.n; k.basebit = key->basebit; k.iks_t = key->t;
+    k.stride = e->ksk_stride; k.zero_row = key->n_rows; k.n_in = e->p.n; k.count = c;
+    CU(ks_launch(k, e->stream));
+    e->launches++;
     CU(cudaMemcpyAsync(out + base * w, sl.out.p, c * w * 4, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
   }

@@ -36,6 +36,7 @@ struct KsArgs {
   const uint32_t *ext;   // [count][N+1] extracted level-1 samples
   uint32_t *out;         // [count][n+1]
   uint32_t n, basebit, iks_t, stride, zero_row;
+  uint32_t n_in;         // input dimension: ext is [count][n_in+1] (N for K4, n for re-encryption)
   size_t count;
 };
 cudaError_t ks_launch(const KsArgs &args, cudaStream_t stream);

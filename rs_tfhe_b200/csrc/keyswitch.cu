@@ -21,8 +21,8 @@ namespace {
 constexpr int KS_B = 8;
 
 __global__ void __launch_bounds__(320) keyswitch_kernel(const KsArgs a) {
-  extern __shared__ uint32_t s_src[];  // [KS_B][1024] : a_i + PREC_OFFSET
-  const uint32_t N = br::kN;
+  extern __shared__ uint32_t s_src[];  // [KS_B][n_in] : a_i + PREC_OFFSET
+  const uint32_t N = a.n_in;  // 1024 for the bootstrap key switch, n for proxy re-encryption
   const size_t ct0 = (size_t)blockIdx.x * KS_B;
   const uint32_t prec = 1u << (32 - (1 + a.basebit * a.iks_t));
   for (int b = 0; b < KS_B; b++) {
@@ -167,12 +167,13 @@ cudaError_t ks_launch(const KsArgs &args, cudaStream_t stream) {
   const int threads = (int)((stride4 + 31) & ~31u);
   if (threads > 320) return cudaErrorInvalidValue;
   static const bool generic_only = getenv("TFHE_KS_GENERIC") != nullptr;
-  if (args.basebit == 2 && threads <= 192 && !generic_only) {
+  if (args.basebit == 2 && threads <= 192 && !generic_only && args.n_in == br::kN) {
     if (args.iks_t == 7) return launch_base4<7>(args, stream);
     if (args.iks_t == 8) return launch_base4<8>(args, stream);
     if (args.iks_t == 9) return launch_base4<9>(args, stream);
   }
-  const int smem = KS_B * br::kN * 4;
+  const int smem = KS_B * (int)args.n_in * 4;
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;
   const unsigned grid = (unsigned)((args.count + KS_B - 1) / KS_B);
   keyswitch_kernel<<<grid, threads, smem, stream>>>(args);
   return cudaGetLastError();

