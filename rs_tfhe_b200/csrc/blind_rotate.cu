@@ -374,6 +374,272 @@ __global__ void __launch_bounds__(G * 64 + 128, 1) blind_rotate_kernel(const BrA
   }
 }
 
+// ---- V4: six groups per SM ------------------------------------------------------------
+// The 2l digit polynomials of a step (rows 0..2l-1 of BSK[i]) go through the two exchange
+// buffers in PAIRS (a0,a1 | a2,b0 | b1,b2 at l=3), so a step has 3l+3 group barriers.  Between
+// MAC phases the 2x8 complex accumulators are parked in TMEM next to the pass-A twiddles, so
+// passes A and B run with ~100 live registers and the whole kernel fits 160 registers/thread
+// without spills -- which is what lets 12 consumer warps (3 per sub-partition) stay resident.
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+      "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+      "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+// park / restore one output's 8 complex accumulators (32 words) at TMEM column `col`
+__device__ __forceinline__ void park8(uint32_t taddr, const cplx (&a)[8]) {
+  uint32_t r[32];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    r[4 * i + 0] = (uint32_t)__double2loint(a[i].x); r[4 * i + 1] = (uint32_t)__double2hiint(a[i].x);
+    r[4 * i + 2] = (uint32_t)__double2loint(a[i].y); r[4 * i + 3] = (uint32_t)__double2hiint(a[i].y);
+  }
+  tmem_st32(taddr, r);
+}
+__device__ __forceinline__ void unpark8(uint32_t taddr, cplx (&a)[8]) {
+  uint32_t r[32];
+  tmem_ld32(taddr, r);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    a[i].x = __hiloint2double((int)r[4 * i + 1], (int)r[4 * i + 0]);
+    a[i].y = __hiloint2double((int)r[4 * i + 3], (int)r[4 * i + 2]);
+  }
+}
+
+template <int L, int BGBIT>
+__global__ void __launch_bounds__(6 * 64 + 128, 1) blind_rotate_kernel_v4(const BrArgs args) {
+  constexpr int G = 6, STAGES = 3, NBUF = 2;
+  using C = Cfg<L, NBUF>;
+  constexpr int L2 = 2 * L;
+  constexpr bool EXACT = (L == 3 && BGBIT == 6);
+  extern __shared__ __align__(128) uint8_t smem[];
+  cplx *ring = reinterpret_cast<cplx *>(smem);
+  uint8_t *groups = smem + STAGES * kStageBytes;
+  uint64_t *full = reinterpret_cast<uint64_t *>(groups + G * C::kGroupBytes);
+  uint64_t *empty = full + STAGES;
+  uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(empty + STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t n = args.n;
+  const uint32_t grid = gridDim.x;
+  const uint32_t per_round = grid * G;
+  const uint32_t rounds = (uint32_t)((args.count + per_round - 1) / per_round);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 2 * G);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
+        smem_u32(tmem_base_s)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+
+  if (warp >= 2 * G) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if (warp == 2 * G && lane == 0) {
+      const uint8_t *src0 = reinterpret_cast<const uint8_t *>(args.bsk);
+      uint32_t stage = 0, parity = 0;
+      const uint32_t rows = n * L2;
+      for (uint32_t rd = 0; rd < rounds; rd++)
+        for (uint32_t row = 0; row < rows; row++) {
+          mbar_wait_backoff(&empty[stage], parity ^ 1);
+          mbar_arrive_expect_tx(&full[stage], kStageBytes);
+          tma_load_1d(reinterpret_cast<uint8_t *>(ring) + stage * kStageBytes,
+                      src0 + (size_t)row * kStageBytes, kStageBytes, &full[stage]);
+          if (++stage == STAGES) { stage = 0; parity ^= 1; }
+        }
+    }
+    return;
+  }
+
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
+  const int g = warp >> 1;
+  const int tid = threadIdx.x & 63;
+  uint8_t *gbase = groups + g * C::kGroupBytes;
+  uint32_t *acc = reinterpret_cast<uint32_t *>(gbase);
+  cplx *exch = reinterpret_cast<cplx *>(gbase + C::kAccBytes);
+  uint16_t *abar_s = reinterpret_cast<uint16_t *>(gbase + C::kAccBytes + C::kExchBytes);
+
+  // TMEM columns of this thread: [0,32) pass-A twiddles, [32,64) racc[0], [64,96) racc[1]
+  const uint32_t taddr = *tmem_base_s + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * 96u;
+  cplx tb1, tb2, tb4;
+  {
+    const cplx *twb = args.tw_b + (tid & 7) * 8;
+    tb1 = twb[1]; tb2 = twb[2]; tb4 = twb[4];
+    cplx ta[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) ta[k] = args.tw_a[tid * 8 + k];
+    tmem_st_ta(taddr, ta);
+  }
+
+  const uint32_t w = n + 1;
+  uint32_t stage = 0, parity = 0;
+
+  for (uint32_t rd = 0; rd < rounds; rd++) {
+    const size_t ct = ((size_t)rd * G + g) * grid + blockIdx.x;
+    const bool active = ct < args.count;
+
+    if (active) {
+      uint32_t ca = 1, cb = 0, off = 0;
+      const uint32_t *A, *B;
+      if (args.op >= 0 || args.ops) {
+        int op = args.ops ? (int)args.ops[ct] : args.op;
+        ca = (uint32_t)c_gate_ca[op]; cb = (uint32_t)c_gate_cb[op]; off = c_gate_off[op];
+        A = args.in + ct * 2 * w;
+        B = A + w;
+      } else {
+        A = args.in + ct * w;
+        B = A;
+      }
+      for (uint32_t i = tid; i < n; i += 64) {
+        uint32_t v = ca * A[i] + cb * B[i];
+        abar_s[i] = (uint16_t)((uint32_t)(v + (1u << 20)) >> 21);
+      }
+      uint32_t bw = ca * A[n] + cb * B[n] + off;
+      uint32_t b_tilda = (uint32_t)(2 * kN - (((uint64_t)bw + (1u << 20)) >> 21));
+      const int tvi = args.tv_index ? args.tv_index[ct] : args.tv_default;
+      const uint32_t *tv = args.tv + (size_t)tvi * 2 * kN;
+      for (int x = tid; x < 2 * kN; x += 64)
+        acc[x] = rot_coeff(tv + (x & ~(kN - 1)), x & (kN - 1), b_tilda);
+    }
+    group_sync(g);
+
+    for (uint32_t i = 0; i < n; i++) {
+      if (active) {
+        const uint32_t abar = abar_s[i];
+        // sub-round s: rows 2s, 2s+1 of BSK[i]; row r = digit (r % L) of polynomial (r / L).
+        // The loop stays rolled (one copy of the passes in the instruction cache).
+        cplx racc[2][8];
+#pragma unroll 1
+        for (int s = 0; s < L; s++) {
+          {
+            cplx ta[8];
+            tmem_ld_ta(taddr, ta);
+            uint32_t t_re[8], t_im[8];
+            const int p0 = (2 * s) / L, p1 = (2 * s + 1) / L;
+            load_t(tid, acc + p0 * kN, abar, args.offset, t_re, t_im);
+            fwd_pass_a_rt<BGBIT>(tid, t_re, t_im, ta, exch, (2 * s) % L);
+            if (p1 != p0) load_t(tid, acc + p1 * kN, abar, args.offset, t_re, t_im);
+            fwd_pass_a_rt<BGBIT>(tid, t_re, t_im, ta, exch + kExchStride, (2 * s + 1) % L);
+          }
+          group_sync(g);
+          {
+            cplx tb[8];
+            expand_tb(tb1, tb2, tb4, tb);
+            fwd_pass_b<2>(tid, tb, exch);
+          }
+          group_sync(g);
+          if (s == 0) {
+#pragma unroll
+            for (int o = 0; o < 2; o++)
+#pragma unroll
+              for (int k = 0; k < 8; k++) racc[o][k] = mk(0.0, 0.0);
+          } else {
+            unpark8(taddr + 32, racc[0]);
+            unpark8(taddr + 64, racc[1]);
+          }
+#pragma unroll
+          for (int q = 0; q < 2; q++) {
+            mbar_wait(&full[stage], parity);
+            fwd_pass_c_mac(tid, exch + q * kExchStride, ring + stage * kChunkCplx, racc);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+            if (++stage == STAGES) { stage = 0; parity ^= 1; }
+          }
+          if (s < L - 1) {
+            park8(taddr + 32, racc[0]);
+            park8(taddr + 64, racc[1]);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          }
+          group_sync(g);  // everyone is done reading exch
+        }
+        {
+          cplx tb[8];
+          expand_tb(tb1, tb2, tb4, tb);
+          inv_pass_c(tid, tb, racc, exch);
+        }
+        group_sync(g);
+        inv_pass_b(tid, exch);
+        group_sync(g);
+        {
+          cplx ta[8];
+          tmem_ld_ta(taddr, ta);
+          inv_pass_a<EXACT>(tid, ta, exch, acc);
+        }
+        group_sync(g);
+      } else {
+        for (int c = 0; c < L2; c++) {
+          mbar_wait(&full[stage], parity);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; parity ^= 1; }
+        }
+      }
+    }
+
+    if (active) {
+      if (args.out_mode == BR_OUT_TRLWE) {
+        uint32_t *o = args.out + ct * 2 * kN;
+        for (int x = tid; x < 2 * kN; x += 64) o[x] = acc[x];
+      } else {
+        const uint32_t m = args.out_mode == BR_OUT_EXTRACT ? (uint32_t)kN : n;
+        uint32_t *o = args.out + ct * (m + 1);
+        for (uint32_t x = tid; x <= m; x += 64) {
+          uint32_t v;
+          if (x == 0) v = acc[0];
+          else if (x == m) v = acc[kN];
+          else v = ~acc[m - x];
+          o[x] = v;
+        }
+      }
+    }
+    group_sync(g);
+  }
+  asm volatile("bar.sync 15, %0;" ::"n"(G * 64) : "memory");
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(*tmem_base_s));
+}
+
+template <int L, int BGBIT>
+cudaError_t launch_v4(const BrArgs &args, int num_sms, cudaStream_t stream) {
+  constexpr int G = 6, STAGES = 3;
+  auto kern = blind_rotate_kernel_v4<L, BGBIT>;
+  const int smem = STAGES * kStageBytes + G * Cfg<L, 2>::kGroupBytes + 2 * STAGES * 8 + 16;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  int grid = (int)(args.count < (size_t)num_sms ? args.count : (size_t)num_sms);
+  if (grid < 1) grid = 1;
+  kern<<<grid, G * 64 + 128, smem, stream>>>(args);
+  return cudaGetLastError();
+}
+
 template <int L, int BGBIT, int G, int STAGES, int NBUF, bool TMEM_TW, int RC, int RP>
 cudaError_t launch_v(const BrArgs &args, int num_sms, cudaStream_t stream) {
   auto kern = blind_rotate_kernel<L, BGBIT, G, STAGES, NBUF, TMEM_TW, RC, RP>;
@@ -395,13 +661,14 @@ int br_variant() {
   if (v < 0) {
     const char *e = getenv("TFHE_BR_VARIANT");
     v = e ? atoi(e) : BR_DEFAULT_VARIANT;
-    if (v < 1 || v > 3) v = BR_DEFAULT_VARIANT;
+    if (v < 1 || v > 4) v = BR_DEFAULT_VARIANT;
   }
   return v;
 }
 
 template <int L, int BGBIT>
 cudaError_t launch_t(const BrArgs &args, int num_sms, cudaStream_t stream) {
+  if (br_variant() == 4) return launch_v4<L, BGBIT>(args, num_sms, stream);
   if (br_variant() == 2)
     return launch_v<L, BGBIT, 6, 3, 2, true, 160, 24>(args, num_sms, stream);
   if (br_variant() == 3)  // V1 residency, but twiddles out of the register file (more ILP room)

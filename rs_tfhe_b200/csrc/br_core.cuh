@@ -184,6 +184,28 @@ BR_HD void fwd_pass_a(int tid, const uint32_t (&t_re)[8], const uint32_t (&t_im)
   }
 }
 
+// Same for ONE digit chosen at run time (keeps the V4 kernel's sub-round loop rolled).
+template <int BGBIT>
+BR_HD void fwd_pass_a_rt(int tid, const uint32_t (&t_re)[8], const uint32_t (&t_im)[8],
+                         const cplx (&ta)[8], cplx *exch_buf, int d) {
+  constexpr uint32_t MASK = (1u << BGBIT) - 1u;
+  constexpr int HALFBG = 1 << (BGBIT - 1);
+  const int sh = 32 - (d + 1) * BGBIT;
+  cplx v[8];
+#define BR_LOAD(M)                                                              \
+  {                                                                             \
+    int dre = (int)((t_re[M] >> sh) & MASK) - HALFBG;                            \
+    int dim = (int)((t_im[M] >> sh) & MASK) - HALFBG;                            \
+    v[M] = cmul(mk((double)dre, (double)dim), pre_w<M>());                      \
+  }
+  BR_LOAD(0) BR_LOAD(1) BR_LOAD(2) BR_LOAD(3) BR_LOAD(4) BR_LOAD(5) BR_LOAD(6) BR_LOAD(7)
+#undef BR_LOAD
+  dft8<false>(v);
+  cplx *e = exch_buf + tid + (tid >> 3);
+#pragma unroll
+  for (int k0 = 0; k0 < 8; k0++) e[k0 * 72] = cmul(v[k0], ta[k0]);
+}
+
 // Pass B: thread u = (k0, j0) transforms over j1, twiddle e^{-2 pi i j0 k1/64}.
 template <int NB> BR_HD void fwd_pass_b(int tid, const cplx (&tb)[8], cplx *exch) {
   const int k0 = tid >> 3, j0 = tid & 7;
