@@ -116,6 +116,14 @@ int tfhe_engine_alloc_cloud_key(tfhe_engine *e);
 int tfhe_engine_cloud_key_blob(tfhe_engine *e, void **device_ptr, size_t *bytes);
 int tfhe_engine_commit_cloud_key(tfhe_engine *e, uint32_t decomposition_offset);
 
+/* Blob/wire format (the reference has no serialization at all): the device-resident
+ * key as one self-describing buffer = 64-byte header {magic "TFHEB200", version, params,
+ * decomposition_offset, lut slots in use, payload bytes} + the device blob verbatim.  Lets a
+ * re-laid-out key be checkpointed or shipped to another host/rank without the reference layout. */
+size_t tfhe_engine_cloud_key_export_bytes(tfhe_engine *e);
+int tfhe_engine_export_cloud_key(tfhe_engine *e, void *host_buf, size_t bytes);
+int tfhe_engine_import_cloud_key(tfhe_engine *e, const void *host_buf, size_t bytes);
+
 /* ---- the hot path, host buffers (H2D + kernels + D2H inside the call) ---- */
 /* Replaces: gates::batch_{nand,and,or,xor,nor,xnor}[_with_railgun]
  * (gates.rs:352-547) and, with count==1, Gates::{nand,...,or_yn} (gates.rs:54-150). */

@@ -152,6 +152,10 @@ def _load():
     L.tfhe_reenc_key_destroy.argtypes = [vp]
     L.tfhe_reenc_key_destroy.restype = None
     L.tfhe_batch_reencrypt.argtypes = [vp, vp, u32p, u32p, C.c_size_t]
+    L.tfhe_engine_cloud_key_export_bytes.argtypes = [vp]
+    L.tfhe_engine_cloud_key_export_bytes.restype = C.c_size_t
+    L.tfhe_engine_export_cloud_key.argtypes = [vp, vp, C.c_size_t]
+    L.tfhe_engine_import_cloud_key.argtypes = [vp, vp, C.c_size_t]
     L.tfhe_probe_fp64_tflops.argtypes = [vp, C.POINTER(C.c_double)]
     if L.tfhe_abi_version() != 1:
         raise EngineError("libtfhe_b200.so ABI version mismatch")
@@ -251,6 +255,18 @@ class CudaBootstrap:
 
     def commit_cloud_key(self, decomposition_offset: int) -> None:
         _check(_load().tfhe_engine_commit_cloud_key(self._h, C.c_uint32(decomposition_offset)))
+
+    def export_cloud_key(self) -> np.ndarray:
+        """The device-resident key as one self-describing byte buffer (header + device blob)."""
+        nbytes = _load().tfhe_engine_cloud_key_export_bytes(self._h)
+        buf = np.empty(nbytes, dtype=np.uint8)
+        _check(_load().tfhe_engine_export_cloud_key(self._h, _ptr(buf), nbytes))
+        return buf
+
+    def import_cloud_key(self, buf: np.ndarray) -> None:
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        _check(_load().tfhe_engine_import_cloud_key(self._h, _ptr(buf), buf.size))
+        self._key = None
 
     def _bind(self, cloud_key: Optional[CloudKey]) -> None:
         if cloud_key is not None and cloud_key is not self._key:

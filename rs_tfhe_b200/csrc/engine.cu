@@ -436,6 +436,66 @@ int tfhe_engine_commit_cloud_key(tfhe_engine *e, uint32_t decomposition_offset) 
   return TFHE_OK;
 }
 
+namespace {
+struct BlobHeader {
+  char magic[8];
+  uint32_t version, n, N, l, bgbit, basebit, iks_t, decomposition_offset, n_lut, reserved;
+  uint64_t payload_bytes;
+  uint8_t pad[8];
+};
+static_assert(sizeof(BlobHeader) == 64, "header is 64 bytes");
+}  // namespace
+
+size_t tfhe_engine_cloud_key_export_bytes(tfhe_engine *e) {
+  return e ? sizeof(BlobHeader) + e->blob_bytes : 0;
+}
+
+int tfhe_engine_export_cloud_key(tfhe_engine *e, void *host_buf, size_t bytes) {
+  if (!e || !host_buf) return fail(TFHE_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (!e->key_loaded) return fail(TFHE_ERR_NO_KEY, "cloud key not loaded");
+  if (bytes < sizeof(BlobHeader) + e->blob_bytes) return fail(TFHE_ERR_INVALID, "buffer too small");
+  CU(cudaSetDevice(e->dev));
+  BlobHeader hd{};
+  memcpy(hd.magic, "TFHEB200", 8);
+  hd.version = TFHE_B200_ABI_VERSION;
+  hd.n = e->p.n; hd.N = e->p.N; hd.l = e->p.l; hd.bgbit = e->p.bgbit; hd.basebit = e->p.basebit;
+  hd.iks_t = e->p.iks_t; hd.decomposition_offset = e->decomp_offset; hd.n_lut = (uint32_t)e->n_lut;
+  hd.payload_bytes = e->blob_bytes;
+  memcpy(host_buf, &hd, sizeof(hd));
+  CU(cudaMemcpyAsync(static_cast<uint8_t *>(host_buf) + sizeof(hd), e->blob, e->blob_bytes,
+                     cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return TFHE_OK;
+}
+
+int tfhe_engine_import_cloud_key(tfhe_engine *e, const void *host_buf, size_t bytes) {
+  if (!e || !host_buf) return fail(TFHE_ERR_INVALID, "null argument");
+  if (bytes < sizeof(BlobHeader)) return fail(TFHE_ERR_INVALID, "truncated blob");
+  BlobHeader hd;
+  memcpy(&hd, host_buf, sizeof(hd));
+  if (memcmp(hd.magic, "TFHEB200", 8) != 0 || hd.version != TFHE_B200_ABI_VERSION)
+    return fail(TFHE_ERR_INVALID, "not a tfhe_b200 key blob (or wrong version)");
+  const tfhe_params &p = e->p;
+  if (hd.n != p.n || hd.N != p.N || hd.l != p.l || hd.bgbit != p.bgbit || hd.basebit != p.basebit ||
+      hd.iks_t != p.iks_t)
+    return fail(TFHE_ERR_INVALID, "blob parameters differ from the engine's");
+  std::lock_guard<std::mutex> lock(e->mu);
+  CU(cudaSetDevice(e->dev));
+  int rc = ensure_blob(e);
+  if (rc != TFHE_OK) return rc;
+  if (hd.payload_bytes != e->blob_bytes || bytes < sizeof(hd) + hd.payload_bytes)
+    return fail(TFHE_ERR_INVALID, "blob size mismatch");
+  if (hd.n_lut < 1 || hd.n_lut > (uint32_t)kMaxLut) return fail(TFHE_ERR_INVALID, "bad lut count");
+  CU(cudaMemcpyAsync(e->blob, static_cast<const uint8_t *>(host_buf) + sizeof(hd), e->blob_bytes,
+                     cudaMemcpyHostToDevice, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  e->decomp_offset = hd.decomposition_offset;
+  e->n_lut = (int)hd.n_lut;
+  e->key_loaded = true;
+  return TFHE_OK;
+}
+
 int tfhe_batch_gate(tfhe_engine *e, tfhe_gate op, const uint32_t *in_pairs, uint32_t *out,
                     size_t count) {
   if (!e) return fail(TFHE_ERR_INVALID, "null engine");

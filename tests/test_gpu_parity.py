@@ -249,3 +249,31 @@ def test_proxy_reencryption_p0(eng128):
     assert np.array_equal(got, ref)
     assert np.array_equal(bob.decrypt_bool(got), bits)
     key.close()
+
+
+def test_cloud_key_blob_export_import(eng128, tmp_path):
+    """the re-laid-out key round-trips through the blob format (via a file) into a
+    fresh engine, LUT slots included, and evaluates identically."""
+    K, _, e = eng128
+    lut_id, lut_b = e.lut_generate([1, 0], 2)
+    blob = e.export_cloud_key()
+    assert bytes(blob[:8]) == b"TFHEB200"
+    path = tmp_path / "key.blob"
+    blob.tofile(path)
+    e2 = T.CudaBootstrap(T.SECURITY_128_BIT, 0)
+    try:
+        e2.import_cloud_key(np.fromfile(path, dtype=np.uint8))
+        rng = O.Rng(7)
+        pairs = bool_pairs(K, [1, 0, 1], [1, 1, 0], rng)
+        assert np.array_equal(e2.batch_gate("XOR", pairs), e.batch_gate("XOR", pairs))
+        ct = K.encrypt_message([0, 1], 2, rng)
+        assert np.array_equal(e2.batch_bootstrap_lut(lut_id, ct), K.batch_bootstrap(ct, lut_b=lut_b))
+        bad = blob.copy(); bad[0] ^= 1
+        with pytest.raises(T.EngineError):
+            e2.import_cloud_key(bad)
+        e80 = T.CudaBootstrap(T.SECURITY_80_BIT, 0)
+        with pytest.raises(T.EngineError, match="parameters differ"):
+            e80.import_cloud_key(blob)
+        e80.close()
+    finally:
+        e2.close()

@@ -1,0 +1,24 @@
+"""Every selectable kernel variant stays bit-exact: the experimental blind-rotation variants
+(TFHE_BR_VARIANT=1,2,4; 3 is the default) and the row-walk key switch (TFHE_KS_VARIANT=rows,
+TFHE_KS_GENERIC=1) run tools/sanitize.py -- mixed gates, LUT bootstrap, blind rotate +
+extract/key switch, each compared word for word with the oracle -- in their own process
+(the selectors are read once per process)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("env", [
+    {"TFHE_BR_VARIANT": "1"}, {"TFHE_BR_VARIANT": "2"}, {"TFHE_BR_VARIANT": "4"},
+    {"TFHE_KS_VARIANT": "rows"}, {"TFHE_KS_VARIANT": "rows", "TFHE_KS_GENERIC": "1"},
+], ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
+def test_variant_bit_exact(env):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sanitize.py")],
+                       env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "gates equal: True" in r.stdout and "lut equal: True" in r.stdout and "ks equal: True" in r.stdout
