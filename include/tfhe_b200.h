@@ -107,6 +107,14 @@ int tfhe_probe_fp64_tflops(tfhe_engine *e, double *tflops_out);
 int tfhe_engine_load_cloud_key(tfhe_engine *e, uint32_t decomposition_offset,
                                const uint32_t *testvec_a, const uint32_t *testvec_b,
                                const uint32_t *ksk, const double *bsk);
+/* Replaces: key::CloudKey::new(&SecretKey) (src/key.rs:59-66: gen_key_switching_key :102-122 +
+ * gen_bootstrapping_key :128-156, TRGSW encryption trgsw.rs:29-68) ON THE DEVICE.
+ * s0 = SecretKey.key_lv0 (n words of 0/1), s1 = key_lv1 (N words); alpha_lv0 = KSK_ALPHA,
+ * alpha_lv1 = BSK_ALPHA (params.rs:468-469).  The reference's RNG is unseeded, so the key is not
+ * comparable bit for bit; it is generated with Philox4x32-10 from `seed` directly in the device
+ * layout.  The test vector and decomposition offset are the standard ones (key.rs:78-100). */
+int tfhe_engine_generate_cloud_key(tfhe_engine *e, const uint32_t *s0, const uint32_t *s1,
+                                   double alpha_lv0, double alpha_lv1, uint64_t seed);
 /* Multi-GPU: the device-resident, re-laid-out key is one contiguous blob.  Rank
  * 0 loads it with tfhe_engine_load_cloud_key; the other ranks call
  * tfhe_engine_alloc_cloud_key, receive the blob (e.g. ncclBroadcast over

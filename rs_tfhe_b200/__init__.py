@@ -156,6 +156,7 @@ def _load():
     L.tfhe_engine_cloud_key_export_bytes.restype = C.c_size_t
     L.tfhe_engine_export_cloud_key.argtypes = [vp, vp, C.c_size_t]
     L.tfhe_engine_import_cloud_key.argtypes = [vp, vp, C.c_size_t]
+    L.tfhe_engine_generate_cloud_key.argtypes = [vp, u32p, u32p, C.c_double, C.c_double, C.c_uint64]
     L.tfhe_probe_fp64_tflops.argtypes = [vp, C.POINTER(C.c_double)]
     if L.tfhe_abi_version() != 1:
         raise EngineError("libtfhe_b200.so ABI version mismatch")
@@ -243,6 +244,15 @@ class CudaBootstrap:
             self._h, C.c_uint32(ck.decomposition_offset), _ptr(_u32(ck.blind_rotate_testvec_a)),
             _ptr(_u32(ck.blind_rotate_testvec_b)), _ptr(ksk), _ptr(bsk)))
         self._key = ck
+
+    def generate_cloud_key(self, key_lv0, key_lv1, seed: int) -> None:
+        """key::CloudKey::new(&secret_key) (src/key.rs:59-66) on the device: KSK + Fourier BSK are
+        generated straight into the device layout (Philox4x32-10 keyed by `seed`)."""
+        p = self.params
+        s0, s1 = _u32(key_lv0, (p.n,)), _u32(key_lv1, (N,))
+        _check(_load().tfhe_engine_generate_cloud_key(self._h, _ptr(s0), _ptr(s1), p.alpha_lv0,
+                                                      p.alpha_lv1, C.c_uint64(seed)))
+        self._key = None
 
     def alloc_cloud_key(self) -> None:
         _check(_load().tfhe_engine_alloc_cloud_key(self._h))

@@ -184,6 +184,29 @@ BR_HD void fwd_pass_a(int tid, const uint32_t (&t_re)[8], const uint32_t (&t_im)
   }
 }
 
+// Pass A on full 32-bit torus coefficients (key generation: trlwe.rs:91-96 / klemsa.rs:88-117
+// applied to a TRLWE row instead of a digit polynomial).  x_re[m] = coefficient 64m+tid,
+// x_im[m] = coefficient 64m+tid+512, read as i32 (klemsa.rs:97-98).
+BR_HD void fwd_pass_a_i32(int tid, const uint32_t (&x_re)[8], const uint32_t (&x_im)[8],
+                          const cplx (&ta)[8], cplx *exch_buf) {
+  cplx v[8];
+#define BR_LOAD(M) v[M] = cmul(mk((double)(int32_t)x_re[M], (double)(int32_t)x_im[M]), pre_w<M>());
+  BR_LOAD(0) BR_LOAD(1) BR_LOAD(2) BR_LOAD(3) BR_LOAD(4) BR_LOAD(5) BR_LOAD(6) BR_LOAD(7)
+#undef BR_LOAD
+  dft8<false>(v);
+  cplx *e = exch_buf + tid + (tid >> 3);
+#pragma unroll
+  for (int k0 = 0; k0 < 8; k0++) e[k0 * 72] = cmul(v[k0], ta[k0]);
+}
+
+// Pass C alone: thread v = (k0, k1) ends with bins k0+8*k1+64*k2 in out[k2].
+BR_HD void fwd_pass_c(int tid, const cplx *exch_d, cplx (&out)[8]) {
+  const cplx *e = exch_d + tid * 9;
+#pragma unroll
+  for (int j0 = 0; j0 < 8; j0++) out[j0] = e[j0];
+  dft8<false>(out);
+}
+
 // Same for ONE digit chosen at run time (keeps the V4 kernel's sub-round loop rolled).
 template <int BGBIT>
 BR_HD void fwd_pass_a_rt(int tid, const uint32_t (&t_re)[8], const uint32_t (&t_im)[8],

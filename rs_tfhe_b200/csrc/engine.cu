@@ -411,6 +411,52 @@ int tfhe_engine_load_cloud_key(tfhe_engine *e, uint32_t decomposition_offset,
   return TFHE_OK;
 }
 
+int tfhe_engine_generate_cloud_key(tfhe_engine *e, const uint32_t *s0, const uint32_t *s1,
+                                   double alpha_lv0, double alpha_lv1, uint64_t seed) {
+  if (!e || !s0 || !s1) return fail(TFHE_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lock(e->mu);
+  CU(cudaSetDevice(e->dev));
+  int rc = ensure_blob(e);
+  if (rc != TFHE_OK) return rc;
+  const tfhe_params &p = e->p;
+  // scratch: s0 | s1 | spectrum(s1) | KSK in the reference row layout
+  const size_t off_s1 = align_up((size_t)p.n * 4, 256);
+  const size_t off_spec = align_up(off_s1 + TFHE_N * 4, 256);
+  const size_t off_ksk = align_up(off_spec + 512 * sizeof(cplx), 256);
+  const size_t ksk_ref_bytes = (size_t)e->ksk_rows * (p.n + 1) * 4;
+  CU(e->s_misc.reserve(off_ksk + ksk_ref_bytes));
+  uint8_t *sc = static_cast<uint8_t *>(e->s_misc.p);
+  CU(cudaMemcpyAsync(sc, s0, (size_t)p.n * 4, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMemcpyAsync(sc + off_s1, s1, TFHE_N * 4, cudaMemcpyHostToDevice, e->stream));
+  uint32_t *d_ksk_ref = reinterpret_cast<uint32_t *>(sc + off_ksk);
+  CU(keygen_launch(e->tw_a, e->tw_b, reinterpret_cast<const uint32_t *>(sc),
+                   reinterpret_cast<const uint32_t *>(sc + off_s1),
+                   reinterpret_cast<cplx *>(sc + off_spec), reinterpret_cast<cplx *>(e->blob),
+                   d_ksk_ref, p.n, p.l, p.bgbit, p.basebit, p.iks_t, alpha_lv0, alpha_lv1, seed,
+                   e->stream));
+  CU(ksk_relayout_launch(d_ksk_ref, reinterpret_cast<uint32_t *>(e->blob + e->off_ksk), e->ksk_rows,
+                         p.n, e->ksk_stride, e->stream));
+  e->launches += 4;
+  if (e->has_kmma) {
+    CU(ksk_mma_relayout_launch(d_ksk_ref, reinterpret_cast<uint32_t *>(e->blob + e->off_kmma), p.n,
+                               p.iks_t, e->stream));
+    e->launches++;
+  }
+  // key.rs:91-100 (test vector) and :78-89 (decomposition offset)
+  std::vector<uint32_t> tv(2 * TFHE_N, 0u);
+  for (int x = 0; x < TFHE_N; x++) tv[TFHE_N + x] = 0x20000000u;
+  CU(cudaMemsetAsync(e->tv(), 0, (size_t)kMaxLut * 2 * TFHE_N * 4, e->stream));
+  CU(cudaMemcpyAsync(e->tv(), tv.data(), tv.size() * 4, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  e->s_misc.release();
+  uint32_t offset = 0;
+  for (uint32_t i = 0; i < p.l; i++) offset += (1u << (p.bgbit - 1)) << (32 - (i + 1) * p.bgbit);
+  e->decomp_offset = offset;
+  e->n_lut = 1;
+  e->key_loaded = true;
+  return TFHE_OK;
+}
+
 int tfhe_engine_alloc_cloud_key(tfhe_engine *e) {
   if (!e) return fail(TFHE_ERR_INVALID, "null engine");
   std::lock_guard<std::mutex> lock(e->mu);

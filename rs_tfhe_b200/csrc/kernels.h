@@ -68,3 +68,9 @@ cudaError_t lut_generate_launch(const uint32_t *d_f_table, uint32_t modulus, dou
 cudaError_t extract_launch(const uint32_t *d_trlwe, uint32_t *d_ext, size_t count,
                            cudaStream_t stream);
 cudaError_t fp64_probe_launch(double *d_sink, int blocks, int iters, cudaStream_t stream);
+
+// K6 (keygen.cu): cloud-key generation on the device
+cudaError_t keygen_launch(const cplx *tw_a, const cplx *tw_b, const uint32_t *d_s0,
+                          const uint32_t *d_s1, cplx *d_s1_spec, cplx *d_bsk, uint32_t *d_ksk_ref,
+                          uint32_t n, uint32_t l, uint32_t bgbit, uint32_t basebit, uint32_t t,
+                          double alpha_lv0, double alpha_lv1, uint64_t seed, cudaStream_t stream);

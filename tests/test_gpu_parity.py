@@ -277,3 +277,65 @@ def test_cloud_key_blob_export_import(eng128, tmp_path):
         e80.close()
     finally:
         e2.close()
+
+
+def test_device_keygen_structure_and_function():
+    """SURVEY 8(f1): CloudKey::new on the device.  The reference's RNG is unseeded, so the check
+    is structural and exact: every generated TRGSW row, pulled back from the device blob and
+    inverse-transformed, satisfies b - a*s1 = noise + gadget term (exact integer product), KSK
+    rows decrypt to k*s1_i/2^((j+1)basebit) within the noise, and gates evaluated with the
+    device-made key decrypt correctly with the expected PBS noise level."""
+    from test_fft_layout_model import inverse_model
+    K, _ = keys("128")
+    p = K.params
+    e = T.CudaBootstrap(T.SECURITY_128_BIT, 0)
+    try:
+        e.generate_cloud_key(K.s0, K.s1, seed=0xC0FFEE)
+        blob = e.export_cloud_key()[64:]
+        l2 = 2 * p.l
+        bsk = blob[: p.n * l2 * 1024 * 16].view(np.float64).reshape(p.n, l2, 8, 2, 64, 2)
+        s1 = K.s1
+        for (i, r) in [(0, 0), (0, 3), (5, 2), (699, 5), (123, 1)]:
+            polys = []
+            for o in range(2):
+                G = bsk[i, r, :, o, :, 0].T + 1j * bsk[i, r, :, o, :, 1].T     # [v][k2]
+                x = inverse_model(G)
+                assert np.abs(x - np.round(x)).max() < 1e-3
+                polys.append((np.round(x).astype(np.int64) & 0xFFFFFFFF).astype(np.uint32))
+            a, b = polys
+            phase = (b.astype(np.int64) - O.poly_mul_exact(a, s1).astype(np.int64)) & 0xFFFFFFFF
+            gad = int(K.s0[i]) << (32 - ((r % p.l) + 1) * p.bgbit)
+            if r >= p.l:
+                phase[0] = (phase[0] - gad) & 0xFFFFFFFF
+            else:
+                phase = (phase + gad * s1.astype(np.int64)) & 0xFFFFFFFF
+            noise = ((phase + 2**31) % 2**32 - 2**31) / 2.0**32
+            assert np.abs(noise).max() < 8 * p.alpha_lv1, (i, r)
+            assert 0.5 * p.alpha_lv1 < noise.std() < 1.5 * p.alpha_lv1, (i, r)
+            assert len(np.unique(a)) > 1000                                  # a is uniform, not degenerate
+        # KSK rows (row layout region follows the BSK, 256-byte aligned)
+        off = (p.n * l2 * 1024 * 16 + 255) // 256 * 256
+        stride = (p.n + 1 + 3) // 4 * 4
+        ksk = blob[off: off + p.ksk_rows * stride * 4].view(np.uint32).reshape(p.ksk_rows, stride)
+        for (i, j, k) in [(0, 0, 1), (17, 3, 2), (1023, 8, 3), (500, 5, 0)]:
+            row = ksk[(i * p.iks_t + j) * 4 + k, : p.n + 1]
+            if k == 0:
+                assert not row.any()
+                continue
+            ph = int(K.phase(row[None])[0])
+            want = (k * int(K.s1[i])) << (32 - (j + 1) * p.basebit)
+            d = ((ph - want + 2**31) % 2**32 - 2**31) / 2.0**32
+            assert abs(d) < 8 * p.alpha_lv0
+        # functional: truth tables + noise level of 4096 random gates
+        r_ = np.random.default_rng(9)
+        a_ = r_.integers(0, 2, 4096).astype(bool)
+        b_ = r_.integers(0, 2, 4096).astype(bool)
+        pairs = np.stack([K.encrypt_bool_batch(a_, 71), K.encrypt_bool_batch(b_, 72)], axis=1)
+        out = e.batch_gate("NAND", pairs)
+        assert np.array_equal(K.decrypt_bool_batch(out), ~(a_ & b_))
+        ph = K.phase_batch(out).astype(np.int64)
+        ideal = np.where(~(a_ & b_), 0x20000000, 0xE0000000)
+        err = ((ph - ideal + 2**31) % 2**32 - 2**31) / 2.0**32
+        assert 0.007 < err.std() < 0.015
+    finally:
+        e.close()
