@@ -135,6 +135,48 @@ __device__ __forceinline__ void tmem_ld_ta(uint32_t taddr, cplx (&ta)[8]) {
   }
 }
 
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+      "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+      "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+// park / restore one output's 8 complex accumulators (32 words) at TMEM column `col`
+__device__ __forceinline__ void park8(uint32_t taddr, const cplx (&a)[8]) {
+  uint32_t r[32];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    r[4 * i + 0] = (uint32_t)__double2loint(a[i].x); r[4 * i + 1] = (uint32_t)__double2hiint(a[i].x);
+    r[4 * i + 2] = (uint32_t)__double2loint(a[i].y); r[4 * i + 3] = (uint32_t)__double2hiint(a[i].y);
+  }
+  tmem_st32(taddr, r);
+}
+__device__ __forceinline__ void unpark8(uint32_t taddr, cplx (&a)[8]) {
+  uint32_t r[32];
+  tmem_ld32(taddr, r);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    a[i].x = __hiloint2double((int)r[4 * i + 1], (int)r[4 * i + 0]);
+    a[i].y = __hiloint2double((int)r[4 * i + 3], (int)r[4 * i + 2]);
+  }
+}
+
 template <int L, int NBUF> struct Cfg {
   static constexpr int kAccBytes = 2 * kN * 4;
   static constexpr int kExchBytes = NBUF * kExchStride * 16;
@@ -146,7 +188,8 @@ template <int L, int NBUF> struct Cfg {
 //   V1: G=4 groups, 3 exchange buffers, twiddles in registers   (consumers 232 regs)
 //   V2: G=6 groups, 2 exchange buffers (digits in sub-rounds of <=2), pass-A twiddles in
 //       TMEM, pass-B twiddles rebuilt from three base values     (consumers 160 regs)
-template <int L, int BGBIT, int G, int STAGES, int NBUF, bool TMEM_TW, int REGS_CONS, int REGS_PROD>
+template <int L, int BGBIT, int G, int STAGES, int NBUF, bool TMEM_TW, int REGS_CONS, int REGS_PROD,
+          bool PARK = false>
 __global__ void __launch_bounds__(G * 64 + 128, 1) blind_rotate_kernel(const BrArgs args) {
   using C = Cfg<L, NBUF>;
   constexpr int L2 = 2 * L;
@@ -175,7 +218,7 @@ __global__ void __launch_bounds__(G * 64 + 128, 1) blind_rotate_kernel(const BrA
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (TMEM_TW && warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
         smem_u32(tmem_base_s)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -226,7 +269,7 @@ __global__ void __launch_bounds__(G * 64 + 128, 1) blind_rotate_kernel(const BrA
       cplx ta[8];
 #pragma unroll
       for (int k = 0; k < 8; k++) ta[k] = args.tw_a[tid * 8 + k];
-      taddr = *tmem_base_s + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * 32u;
+      taddr = *tmem_base_s + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * 96u;
       tmem_st_ta(taddr, ta);
     } else {
 #pragma unroll
@@ -305,7 +348,16 @@ __global__ void __launch_bounds__(G * 64 + 128, 1) blind_rotate_kernel(const BrA
             fwd_pass_b<ND0>(tid, tb, exch);
           }
           group_sync(g);
+          if (PARK && p == 1) {   // accumulators were parked in TMEM during poly b's passes A/B
+            unpark8(taddr + 32, racc[0]);
+            unpark8(taddr + 64, racc[1]);
+          }
           BR_MAC_DIGITS(ND0)
+          if (PARK && p == 0 && ND1 == 0) {
+            park8(taddr + 32, racc[0]);
+            park8(taddr + 64, racc[1]);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          }
           group_sync(g);
           if constexpr (ND1 > 0) {
             {
@@ -370,7 +422,7 @@ __global__ void __launch_bounds__(G * 64 + 128, 1) blind_rotate_kernel(const BrA
   if constexpr (TMEM_TW) {
     asm volatile("bar.sync 15, %0;" ::"n"(G * 64) : "memory");  // all consumers done with TMEM
     if (warp == 0)
-      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(*tmem_base_s));
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(*tmem_base_s));
   }
 }
 
@@ -380,48 +432,6 @@ __global__ void __launch_bounds__(G * 64 + 128, 1) blind_rotate_kernel(const BrA
 // MAC phases the 2x8 complex accumulators are parked in TMEM next to the pass-A twiddles, so
 // passes A and B run with ~100 live registers and the whole kernel fits 160 registers/thread
 // without spills -- which is what lets 12 consumer warps (3 per sub-partition) stay resident.
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
-      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
-      "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
-      "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-// park / restore one output's 8 complex accumulators (32 words) at TMEM column `col`
-__device__ __forceinline__ void park8(uint32_t taddr, const cplx (&a)[8]) {
-  uint32_t r[32];
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    r[4 * i + 0] = (uint32_t)__double2loint(a[i].x); r[4 * i + 1] = (uint32_t)__double2hiint(a[i].x);
-    r[4 * i + 2] = (uint32_t)__double2loint(a[i].y); r[4 * i + 3] = (uint32_t)__double2hiint(a[i].y);
-  }
-  tmem_st32(taddr, r);
-}
-__device__ __forceinline__ void unpark8(uint32_t taddr, cplx (&a)[8]) {
-  uint32_t r[32];
-  tmem_ld32(taddr, r);
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    a[i].x = __hiloint2double((int)r[4 * i + 1], (int)r[4 * i + 0]);
-    a[i].y = __hiloint2double((int)r[4 * i + 3], (int)r[4 * i + 2]);
-  }
-}
-
 template <int L, int BGBIT>
 __global__ void __launch_bounds__(6 * 64 + 128, 1) blind_rotate_kernel_v4(const BrArgs args) {
   constexpr int G = 6, STAGES = 3, NBUF = 2;
@@ -640,9 +650,9 @@ cudaError_t launch_v4(const BrArgs &args, int num_sms, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
-template <int L, int BGBIT, int G, int STAGES, int NBUF, bool TMEM_TW, int RC, int RP>
+template <int L, int BGBIT, int G, int STAGES, int NBUF, bool TMEM_TW, int RC, int RP, bool PARK = false>
 cudaError_t launch_v(const BrArgs &args, int num_sms, cudaStream_t stream) {
-  auto kern = blind_rotate_kernel<L, BGBIT, G, STAGES, NBUF, TMEM_TW, RC, RP>;
+  auto kern = blind_rotate_kernel<L, BGBIT, G, STAGES, NBUF, TMEM_TW, RC, RP, PARK>;
   const int smem = STAGES * kStageBytes + G * Cfg<L, NBUF>::kGroupBytes + 2 * STAGES * 8 + 16;
   static bool configured = false;  // per instantiation
   if (!configured) {
@@ -661,7 +671,7 @@ int br_variant() {
   if (v < 0) {
     const char *e = getenv("TFHE_BR_VARIANT");
     v = e ? atoi(e) : BR_DEFAULT_VARIANT;
-    if (v < 1 || v > 4) v = BR_DEFAULT_VARIANT;
+    if (v < 1 || v > 5) v = BR_DEFAULT_VARIANT;
   }
   return v;
 }
@@ -669,6 +679,8 @@ int br_variant() {
 template <int L, int BGBIT>
 cudaError_t launch_t(const BrArgs &args, int num_sms, cudaStream_t stream) {
   if (br_variant() == 4) return launch_v4<L, BGBIT>(args, num_sms, stream);
+  if (br_variant() == 5)  // variant 3 + MAC accumulators parked in TMEM across poly b's passes A/B
+    return launch_v<L, BGBIT, 4, 4, 3, true, 232, 40, true>(args, num_sms, stream);
   if (br_variant() == 2)
     return launch_v<L, BGBIT, 6, 3, 2, true, 160, 24>(args, num_sms, stream);
   if (br_variant() == 3)  // V1 residency, but twiddles out of the register file (more ILP room)

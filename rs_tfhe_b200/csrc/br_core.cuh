@@ -57,28 +57,45 @@ BR_HD int phys(int p) { return p + (p >> 3); }
 template <bool INV> BR_HD cplx mul_i(cplx a) {  // * (-i) forward, * (+i) inverse
   return INV ? mk(-a.y, a.x) : mk(a.y, -a.x);
 }
-template <bool INV> BR_HD cplx mul_w1(cplx a) {  // * e^{-+ i pi/4}
-  const double s = 0.70710678118654752440;
-  return INV ? mk((a.x - a.y) * s, (a.x + a.y) * s) : mk((a.x + a.y) * s, (a.y - a.x) * s);
+// * sqrt(2) e^{-+ i pi/4} and * sqrt(2) e^{-+ 3 i pi/4}: the 1/sqrt(2) is applied later inside an FMA
+template <bool INV> BR_HD cplx mul_w1u(cplx a) {
+  return INV ? mk(a.x - a.y, a.x + a.y) : mk(a.x + a.y, a.y - a.x);
 }
-template <bool INV> BR_HD cplx mul_w3(cplx a) {  // * e^{-+ 3 i pi/4}
-  const double s = 0.70710678118654752440;
-  return INV ? mk((-a.x - a.y) * s, (a.x - a.y) * s) : mk((a.y - a.x) * s, (-a.x - a.y) * s);
+template <bool INV> BR_HD cplx mul_w3u(cplx a) {
+  return INV ? mk(-a.x - a.y, a.x - a.y) : mk(a.y - a.x, -a.x - a.y);
 }
+// c + s*q and c - s*q as FMAs
+BR_HD cplx cfma_s(cplx c, double s, cplx q) { return mk(c.x + s * q.x, c.y + s * q.y); }
 
 template <bool INV> BR_HD void dft8(cplx (&v)[8]) {
+  const double s = 0.70710678118654752440;
   cplx a0 = cadd(v[0], v[4]), a4 = csub(v[0], v[4]);
-  cplx a1 = cadd(v[1], v[5]), a5 = mul_w1<INV>(csub(v[1], v[5]));
+  cplx a1 = cadd(v[1], v[5]), p5 = mul_w1u<INV>(csub(v[1], v[5]));
   cplx a2 = cadd(v[2], v[6]), a6 = mul_i<INV>(csub(v[2], v[6]));
-  cplx a3 = cadd(v[3], v[7]), a7 = mul_w3<INV>(csub(v[3], v[7]));
+  cplx a3 = cadd(v[3], v[7]), p7 = mul_w3u<INV>(csub(v[3], v[7]));
   cplx b0 = cadd(a0, a2), b2 = csub(a0, a2);
   cplx b1 = cadd(a1, a3), b3 = mul_i<INV>(csub(a1, a3));
   v[0] = cadd(b0, b1); v[4] = csub(b0, b1);
   v[2] = cadd(b2, b3); v[6] = csub(b2, b3);
+  // odd outputs: the two 1/sqrt(2) twiddles are folded into the last butterfly stage
   cplx c0 = cadd(a4, a6), c2 = csub(a4, a6);
-  cplx c1 = cadd(a5, a7), c3 = mul_i<INV>(csub(a5, a7));
-  v[1] = cadd(c0, c1); v[5] = csub(c0, c1);
-  v[3] = cadd(c2, c3); v[7] = csub(c2, c3);
+  cplx q1 = cadd(p5, p7), q3 = mul_i<INV>(csub(p5, p7));
+  v[1] = cfma_s(c0, s, q1); v[5] = cfma_s(c0, -s, q1);
+  v[3] = cfma_s(c2, s, q3); v[7] = cfma_s(c2, -s, q3);
+}
+
+// (re + i im) * omega^(64 M) and its conjugate form, with the trivial cases spelled out
+// (M = 0: nothing; M = 4: one real factor) so no multiply-by-one/zero is issued
+template <int M> BR_HD cplx pre_w();
+template <int M> BR_HD cplx twist_in(double re, double im) {
+  if (M == 0) return mk(re, im);
+  if (M == 4) { const double s = 0.70710678118654752440; return mk((re - im) * s, (re + im) * s); }
+  return cmul(mk(re, im), pre_w<M>());
+}
+template <int M> BR_HD cplx twist_out(cplx a) {  // a * conj(omega^(64 M))
+  if (M == 0) return a;
+  if (M == 4) { const double s = 0.70710678118654752440; return mk((a.x + a.y) * s, (a.y - a.x) * s); }
+  return cmulc(a, pre_w<M>());
 }
 
 // omega^(64 m) = e^{i pi m/16}: the compile-time part of the twist
@@ -173,7 +190,7 @@ BR_HD void fwd_pass_a(int tid, const uint32_t (&t_re)[8], const uint32_t (&t_im)
   {                                                                             \
     int dre = (int)((t_re[M] >> sh) & MASK) - HALFBG;                            \
     int dim = (int)((t_im[M] >> sh) & MASK) - HALFBG;                            \
-    v[M] = cmul(mk((double)dre, (double)dim), pre_w<M>());                      \
+    v[M] = twist_in<M>((double)dre, (double)dim);                               \
   }
     BR_LOAD(0) BR_LOAD(1) BR_LOAD(2) BR_LOAD(3) BR_LOAD(4) BR_LOAD(5) BR_LOAD(6) BR_LOAD(7)
 #undef BR_LOAD
@@ -190,7 +207,7 @@ BR_HD void fwd_pass_a(int tid, const uint32_t (&t_re)[8], const uint32_t (&t_im)
 BR_HD void fwd_pass_a_i32(int tid, const uint32_t (&x_re)[8], const uint32_t (&x_im)[8],
                           const cplx (&ta)[8], cplx *exch_buf) {
   cplx v[8];
-#define BR_LOAD(M) v[M] = cmul(mk((double)(int32_t)x_re[M], (double)(int32_t)x_im[M]), pre_w<M>());
+#define BR_LOAD(M) v[M] = twist_in<M>((double)(int32_t)x_re[M], (double)(int32_t)x_im[M]);
   BR_LOAD(0) BR_LOAD(1) BR_LOAD(2) BR_LOAD(3) BR_LOAD(4) BR_LOAD(5) BR_LOAD(6) BR_LOAD(7)
 #undef BR_LOAD
   dft8<false>(v);
@@ -219,7 +236,7 @@ BR_HD void fwd_pass_a_rt(int tid, const uint32_t (&t_re)[8], const uint32_t (&t_
   {                                                                             \
     int dre = (int)((t_re[M] >> sh) & MASK) - HALFBG;                            \
     int dim = (int)((t_im[M] >> sh) & MASK) - HALFBG;                            \
-    v[M] = cmul(mk((double)dre, (double)dim), pre_w<M>());                      \
+    v[M] = twist_in<M>((double)dre, (double)dim);                               \
   }
   BR_LOAD(0) BR_LOAD(1) BR_LOAD(2) BR_LOAD(3) BR_LOAD(4) BR_LOAD(5) BR_LOAD(6) BR_LOAD(7)
 #undef BR_LOAD
@@ -301,7 +318,7 @@ BR_HD void inv_pass_a(int tid, const cplx (&ta)[8], const cplx *exch, uint32_t *
     uint32_t *ap = acc + o * kN;
 #define BR_STORE(M)                                                       \
   {                                                                       \
-    cplx y = cmulc(v[M], pre_w<M>());                                     \
+    cplx y = twist_out<M>(v[M]);                                          \
     ap[64 * M + tid] += round_torus<EXACT>(y.x);                          \
     ap[64 * M + tid + kHalf] += round_torus<EXACT>(y.y);                  \
   }

@@ -8,7 +8,7 @@
 // the byte planes are recombined with wrapping shifts in the epilogue, so the result is
 // bit-identical to the reference's wrapping subtractions.
 //
-//   M = ciphertexts (128 per CTA = 8 m16 tiles), N = 4 byte planes x 8 words per warp,
+//   M = ciphertexts (64 per CTA = 4 m16 tiles; two CTAs per SM), N = 4 byte planes x 8 words per warp,
 //   K = (i-block, j, ii, k): 32 per mma.sync.m16n8k32 = 8 coefficients x 4 digit values.
 // A fragments are built in registers from the digits (one 32-bit register = the one-hot over
 // k = 0..3 of one (ct, i, j)); B fragments come from a key copy pre-tiled at upload into exactly
@@ -18,7 +18,13 @@
 
 namespace {
 
-constexpr int KM_MT = 8;       // m16 tiles per CTA
+#ifndef KM_MT_DEF
+#define KM_MT_DEF 4
+#endif
+#ifndef KM_CTAS_DEF
+#define KM_CTAS_DEF 2
+#endif
+constexpr int KM_MT = KM_MT_DEF;       // m16 tiles per CTA
 constexpr int KM_WARPS = 8;    // each warp owns 8 words (32 byte columns) of the output
 constexpr int KM_DEPTH = 8;    // cp.async ring depth in k-steps
 
@@ -39,13 +45,14 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int Nw> __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(Nw) : "memory");
 }
-// one-hot over k = 0..3 in the four bytes of a register; digit 0 selects nothing (trgsw.rs:351)
-__device__ __forceinline__ uint32_t onehot(uint32_t abar, uint32_t sh) {
-  const uint32_t d = (abar >> sh) & 3u;
-  return (1u << (d << 3)) & 0xFFFFFF00u;
+// one-hot over k = 0..3 in the four bytes of a register.  Digit 0 sets byte 0, which meets the
+// k = 0 byte of the B fragment -- forced to zero at upload -- so it selects nothing (trgsw.rs:351).
+// sh3 = (30 - 2j) - 3: the digit lands pre-multiplied by 8.
+__device__ __forceinline__ uint32_t onehot(uint32_t abar, uint32_t sh3) {
+  return 1u << ((abar >> sh3) & 0x18u);
 }
 
-__global__ void __launch_bounds__(KM_WARPS * 32, 1) ks_mma_kernel(const KsMmaArgs a) {
+__global__ void __launch_bounds__(KM_WARPS * 32, KM_CTAS_DEF) ks_mma_kernel(const KsMmaArgs a) {
   extern __shared__ __align__(16) uint8_t km_smem[];
   uint4(*ring)[2][KM_WARPS * 32] =
       reinterpret_cast<uint4(*)[2][KM_WARPS * 32]>(km_smem);  // [slot][b0|b1][thread] : 64 KB
@@ -106,7 +113,7 @@ __global__ void __launch_bounds__(KM_WARPS * 32, 1) ks_mma_kernel(const KsMmaArg
       cp_async_wait<KM_DEPTH - 1>();
       const uint4 B0 = ring[s % KM_DEPTH][0][threadIdx.x];
       const uint4 B1 = ring[s % KM_DEPTH][1][threadIdx.x];
-      const uint32_t sh = 30 - 2 * j;
+      const uint32_t sh = 27 - 2 * j;
 #pragma unroll
       for (int m = 0; m < KM_MT; m++) {
         const uint32_t a0 = onehot(ab[m][0], sh), a1 = onehot(ab[m][1], sh);
