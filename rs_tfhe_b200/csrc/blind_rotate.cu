@@ -650,6 +650,244 @@ cudaError_t launch_v4(const BrArgs &args, int num_sms, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+// ---- latency variant: ONE ciphertext per CTA, its 2l digit transforms spread over l groups ---
+// For small batches (dependent PBS chains, BASELINE config 4) the throughput kernel leaves a
+// ciphertext to one 64-thread group that walks the whole chain (11 k cycles per CMUX).  Here group
+// g of l takes rows 2g, 2g+1 of BSK[i] (digit pair), the groups' partial spectra are summed
+// through shared memory, and groups 0 and 1 run the two inverse transforms in parallel.  The
+// ring has one stage per row (stage r <-> row r), each consumed by exactly one group, so the
+// next step's rows stream in while the inverse runs.  256 threads (l<=3 groups + producer warp),
+// no register rebalancing needed.
+template <int L, int BGBIT>
+__global__ void __launch_bounds__(256, 1) blind_rotate_latency_kernel(const BrArgs args) {
+  constexpr int NG = L;            // cooperating groups
+  constexpr int L2 = 2 * L;
+  constexpr int STAGES = L2;
+  constexpr bool EXACT = (L == 3 && BGBIT == 6);
+  constexpr int kAccBytes = 2 * kN * 4;
+  constexpr int kExchBytes = 2 * kExchStride * 16;  // two buffers per group
+  extern __shared__ __align__(128) uint8_t smem[];
+  cplx *ring = reinterpret_cast<cplx *>(smem);
+  uint32_t *acc = reinterpret_cast<uint32_t *>(smem + STAGES * kStageBytes);
+  uint8_t *exch_base = smem + STAGES * kStageBytes + kAccBytes;
+  uint16_t *abar_s = reinterpret_cast<uint16_t *>(exch_base + NG * kExchBytes);
+  uint64_t *full = reinterpret_cast<uint64_t *>(exch_base + NG * kExchBytes + 2432);
+  uint64_t *empty = full + STAGES;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t n = args.n;
+  const uint32_t grid = gridDim.x;
+  const uint32_t rounds = (uint32_t)((args.count + grid - 1) / grid);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 2);   // the two warps of the one group that owns this row
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp >= 2 * NG) {
+    if (warp == 2 * NG && lane == 0) {
+      const uint8_t *src0 = reinterpret_cast<const uint8_t *>(args.bsk);
+      uint32_t parity = 0;
+      for (uint32_t rd = 0; rd < rounds; rd++)
+        for (uint32_t i = 0; i < n; i++) {
+          for (uint32_t r = 0; r < (uint32_t)L2; r++) {
+            mbar_wait_backoff(&empty[r], parity ^ 1);
+            mbar_arrive_expect_tx(&full[r], kStageBytes);
+            tma_load_1d(reinterpret_cast<uint8_t *>(ring) + r * kStageBytes,
+                        src0 + ((size_t)i * L2 + r) * kStageBytes, kStageBytes, &full[r]);
+          }
+          parity ^= 1;
+        }
+    }
+    return;
+  }
+
+  const int g = warp >> 1;
+  const int tid = threadIdx.x & 63;
+  const int ctid = threadIdx.x;  // 0 .. 64*NG-1 among consumers
+  cplx *exch = reinterpret_cast<cplx *>(exch_base + g * kExchBytes);
+  cplx ta[8], tb[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) { ta[k] = args.tw_a[tid * 8 + k]; tb[k] = args.tw_b[(tid & 7) * 8 + k]; }
+  auto cta_sync = [&]() { asm volatile("bar.sync 8, %0;" ::"n"(64 * NG) : "memory"); };
+
+  const uint32_t w = n + 1;
+  uint32_t parity = 0;
+  const int p0 = (2 * g) / L, p1 = (2 * g + 1) / L;       // polynomials of this group's two rows
+  const int d0 = (2 * g) % L, d1 = (2 * g + 1) % L;       // and their digits
+
+  for (uint32_t rd = 0; rd < rounds; rd++) {
+    const size_t ct = (size_t)rd * grid + blockIdx.x;
+    const bool active = ct < args.count;
+    if (active) {
+      uint32_t ca = 1, cb = 0, off = 0;
+      const uint32_t *A, *B;
+      if (args.op >= 0 || args.ops) {
+        int op = args.ops ? (int)args.ops[ct] : args.op;
+        ca = (uint32_t)c_gate_ca[op]; cb = (uint32_t)c_gate_cb[op]; off = c_gate_off[op];
+        A = args.in + ct * 2 * w;
+        B = A + w;
+      } else {
+        A = args.in + ct * w;
+        B = A;
+      }
+      for (uint32_t i = ctid; i < n; i += 64 * NG) {
+        uint32_t v = ca * A[i] + cb * B[i];
+        abar_s[i] = (uint16_t)((uint32_t)(v + (1u << 20)) >> 21);
+      }
+      uint32_t bw = ca * A[n] + cb * B[n] + off;
+      uint32_t b_tilda = (uint32_t)(2 * kN - (((uint64_t)bw + (1u << 20)) >> 21));
+      const int tvi = args.tv_index ? args.tv_index[ct] : args.tv_default;
+      const uint32_t *tv = args.tv + (size_t)tvi * 2 * kN;
+      for (int x = ctid; x < 2 * kN; x += 64 * NG)
+        acc[x] = rot_coeff(tv + (x & ~(kN - 1)), x & (kN - 1), b_tilda);
+    }
+    cta_sync();
+
+    for (uint32_t i = 0; i < n; i++) {
+      if (active) {
+        const uint32_t abar = abar_s[i];
+        {
+          uint32_t t_re[8], t_im[8];
+          load_t(tid, acc + p0 * kN, abar, args.offset, t_re, t_im);
+          fwd_pass_a_rt<BGBIT>(tid, t_re, t_im, ta, exch, d0);
+          if (p1 != p0) load_t(tid, acc + p1 * kN, abar, args.offset, t_re, t_im);
+          fwd_pass_a_rt<BGBIT>(tid, t_re, t_im, ta, exch + kExchStride, d1);
+        }
+        group_sync(g);
+        fwd_pass_b<2>(tid, tb, exch);
+        group_sync(g);
+        cplx racc[2][8];
+#pragma unroll
+        for (int o = 0; o < 2; o++)
+#pragma unroll
+          for (int k = 0; k < 8; k++) racc[o][k] = mk(0.0, 0.0);
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+          const int row = 2 * g + q;
+          mbar_wait(&full[row], parity);
+          fwd_pass_c_mac(tid, exch + q * kExchStride, ring + row * kChunkCplx, racc);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[row]);
+        }
+        if (NG > 1) {
+          group_sync(g);  // the group is done reading its pass-C inputs
+          // publish this group's partial spectra: [o][v*9 + k2] in its own two buffers
+#pragma unroll
+          for (int o = 0; o < 2; o++)
+#pragma unroll
+            for (int k = 0; k < 8; k++) exch[o * kExchStride + tid * 9 + k] = racc[o][k];
+          cta_sync();
+          if (g < 2) {
+            // group o = g sums the partials of output o and runs its inverse transform
+#pragma unroll
+            for (int k = 0; k < 8; k++) racc[0][k] = mk(0.0, 0.0);
+#pragma unroll
+            for (int gg = 0; gg < NG; gg++) {
+              const cplx *src = reinterpret_cast<const cplx *>(exch_base + gg * kExchBytes) +
+                                g * kExchStride + tid * 9;
+#pragma unroll
+              for (int k = 0; k < 8; k++) racc[0][k] = cadd(racc[0][k], src[k]);
+            }
+          }
+          cta_sync();  // all partials consumed before anyone overwrites an exchange buffer
+          if (g < 2) {
+            cplx *e = exch;  // this group's buffer 0
+            dft8<true>(racc[0]);
+            e[tid * 9] = racc[0][0];
+#pragma unroll
+            for (int j0 = 1; j0 < 8; j0++) e[tid * 9 + j0] = cmulc(racc[0][j0], tb[j0]);
+            group_sync(g);
+            {
+              const int k0 = tid >> 3, j0 = tid & 7;
+              cplx *eb = e + k0 * 72 + j0;
+              cplx v[8];
+#pragma unroll
+              for (int k1 = 0; k1 < 8; k1++) v[k1] = eb[k1 * 9];
+              dft8<true>(v);
+#pragma unroll
+              for (int j1 = 0; j1 < 8; j1++) eb[j1 * 9] = v[j1];
+            }
+            group_sync(g);
+            {
+              const cplx *ea = e + tid + (tid >> 3);
+              cplx v[8];
+#pragma unroll
+              for (int k0 = 0; k0 < 8; k0++) v[k0] = cmulc(ea[k0 * 72], ta[k0]);
+              dft8<true>(v);
+              uint32_t *ap = acc + g * kN;
+#define BR_STORE(M)                                                       \
+  {                                                                       \
+    cplx y = twist_out<M>(v[M]);                                          \
+    ap[64 * M + tid] += round_torus<EXACT>(y.x);                          \
+    ap[64 * M + tid + kHalf] += round_torus<EXACT>(y.y);                  \
+  }
+              BR_STORE(0) BR_STORE(1) BR_STORE(2) BR_STORE(3) BR_STORE(4) BR_STORE(5) BR_STORE(6) BR_STORE(7)
+#undef BR_STORE
+            }
+          }
+          cta_sync();
+        } else {
+          group_sync(g);
+          inv_pass_c(tid, tb, racc, exch);
+          group_sync(g);
+          inv_pass_b(tid, exch);
+          group_sync(g);
+          inv_pass_a<EXACT>(tid, ta, exch, acc);
+          group_sync(g);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+          const int row = 2 * g + q;
+          mbar_wait(&full[row], parity);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[row]);
+        }
+      }
+      parity ^= 1;
+    }
+
+    if (active) {
+      if (args.out_mode == BR_OUT_TRLWE) {
+        uint32_t *o = args.out + ct * 2 * kN;
+        for (int x = ctid; x < 2 * kN; x += 64 * NG) o[x] = acc[x];
+      } else {
+        const uint32_t m = args.out_mode == BR_OUT_EXTRACT ? (uint32_t)kN : n;
+        uint32_t *o = args.out + ct * (m + 1);
+        for (uint32_t x = ctid; x <= m; x += 64 * NG) {
+          uint32_t v;
+          if (x == 0) v = acc[0];
+          else if (x == m) v = acc[kN];
+          else v = ~acc[m - x];
+          o[x] = v;
+        }
+      }
+    }
+    cta_sync();
+  }
+}
+
+template <int L, int BGBIT>
+cudaError_t launch_latency(const BrArgs &args, int num_sms, cudaStream_t stream) {
+  auto kern = blind_rotate_latency_kernel<L, BGBIT>;
+  const int smem = 2 * L * kStageBytes + 2 * kN * 4 + L * 2 * kExchStride * 16 + 2432 + 4 * L * 8 + 16;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  int grid = (int)(args.count < (size_t)num_sms ? args.count : (size_t)num_sms);
+  if (grid < 1) grid = 1;
+  kern<<<grid, 256, smem, stream>>>(args);
+  return cudaGetLastError();
+}
+
 template <int L, int BGBIT, int G, int STAGES, int NBUF, bool TMEM_TW, int RC, int RP, bool PARK = false>
 cudaError_t launch_v(const BrArgs &args, int num_sms, cudaStream_t stream) {
   auto kern = blind_rotate_kernel<L, BGBIT, G, STAGES, NBUF, TMEM_TW, RC, RP, PARK>;
@@ -676,8 +914,20 @@ int br_variant() {
   return v;
 }
 
+// batches this small go to the latency kernel (one ciphertext per SM, l groups each)
+int br_latency_threshold(int num_sms) {
+  static int thr = -2;
+  if (thr == -2) {
+    const char *e = getenv("TFHE_BR_LATENCY_MAX");
+    thr = e ? atoi(e) : -1;
+  }
+  return thr >= 0 ? thr : num_sms;  // measured crossover: 148 gates 2.55 vs 4.04 ms, 296 gates 5.04 vs 4.41 ms
+}
+
 template <int L, int BGBIT>
 cudaError_t launch_t(const BrArgs &args, int num_sms, cudaStream_t stream) {
+  if (L > 1 && args.count <= (size_t)br_latency_threshold(num_sms))
+    return launch_latency<L, BGBIT>(args, num_sms, stream);
   if (br_variant() == 4) return launch_v4<L, BGBIT>(args, num_sms, stream);
   if (br_variant() == 5)  // variant 3 + MAC accumulators parked in TMEM across poly b's passes A/B
     return launch_v<L, BGBIT, 4, 4, 3, true, 232, 40, true>(args, num_sms, stream);

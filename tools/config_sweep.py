@@ -78,8 +78,9 @@ lat = []
 for _ in range(5):
     t = time.perf_counter()
     ct_low = (a_lo + b_lo).astype(np.uint32)
-    s_lo = e.batch_bootstrap_lut(ids["low"][0], ct_low)          # PBS1 and PBS2 share the input
-    carry = e.batch_bootstrap_lut(ids["carry"][0], ct_low)
+    # PBS1 and PBS2 share the input: one batch with per-ciphertext tables (level 1 of the chain)
+    both = e.batch_bootstrap_lut([ids["low"][0], ids["carry"][0]], np.stack([ct_low, ct_low]))
+    s_lo, carry = both[0], both[1]
     ct_hi = (a_hi + b_hi + carry).astype(np.uint32)
     s_hi = e.batch_bootstrap_lut(ids["high"][0], ct_hi)
     lat.append(time.perf_counter() - t)
