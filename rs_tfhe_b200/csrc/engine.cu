@@ -246,7 +246,41 @@ int run_host(tfhe_engine *e, int op, const uint8_t *ops, int lut_id, const uint3
 
 }  // namespace
 
+static int engine_init(tfhe_engine *e, int device_id) {
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device_id));
+  e->num_sms = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+  e->stream = e->own_stream;
+  CU(cudaStreamCreateWithFlags(&e->copy_in, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&e->copy_out, cudaStreamNonBlocking));
+  for (auto &ev : e->ev) CU(cudaEventCreate(&ev));
+  for (auto &sl : e->slot)
+    for (cudaEvent_t *pe : {&sl.h2d_done, &sl.br_start, &sl.br_end, &sl.ks_end, &sl.d2h_done})
+      CU(cudaEventCreate(pe));
+  // twiddles (br_core.cuh): ta[r][k0] = e^{i pi r(1-4k0)/1024}, tb[j][x] = e^{-2 pi i jx/64}
+  std::vector<cplx> ta(64 * 8), tb(8 * 8);
+  for (int r = 0; r < 64; r++)
+    for (int k0 = 0; k0 < 8; k0++) {
+      int idx = ((r * (1 - 4 * k0)) % 2048 + 2048) % 2048;
+      double ang = M_PI * (double)idx / 1024.0;
+      ta[r * 8 + k0] = br::mk(std::cos(ang), std::sin(ang));
+    }
+  for (int j = 0; j < 8; j++)
+    for (int x = 0; x < 8; x++) {
+      double ang = -2.0 * M_PI * (double)((j * x) % 64) / 64.0;
+      tb[j * 8 + x] = br::mk(std::cos(ang), std::sin(ang));
+    }
+  CU(cudaMalloc(reinterpret_cast<void **>(&e->tw_a), ta.size() * sizeof(cplx)));
+  CU(cudaMalloc(reinterpret_cast<void **>(&e->tw_b), tb.size() * sizeof(cplx)));
+  CU(cudaMemcpy(e->tw_a, ta.data(), ta.size() * sizeof(cplx), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(e->tw_b, tb.data(), tb.size() * sizeof(cplx), cudaMemcpyHostToDevice));
+  blob_layout(e);
+  return TFHE_OK;
+}
+
 extern "C" {
+void tfhe_engine_destroy(tfhe_engine *e);
 
 int tfhe_abi_version(void) { return TFHE_B200_ABI_VERSION; }
 const char *tfhe_last_error(void) { return g_err; }
@@ -282,35 +316,14 @@ int tfhe_engine_create(const tfhe_params *params, int device_id, tfhe_engine **o
   if (!e) return fail(TFHE_ERR_ALLOC, "out of host memory");
   e->p = p;
   e->dev = device_id;
-  cudaDeviceProp prop;
-  CU(cudaGetDeviceProperties(&prop, device_id));
-  e->num_sms = prop.multiProcessorCount;
-  CU(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
-  e->stream = e->own_stream;
-  CU(cudaStreamCreateWithFlags(&e->copy_in, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&e->copy_out, cudaStreamNonBlocking));
-  for (auto &ev : e->ev) CU(cudaEventCreate(&ev));
-  for (auto &sl : e->slot)
-    for (cudaEvent_t *pe : {&sl.h2d_done, &sl.br_start, &sl.br_end, &sl.ks_end, &sl.d2h_done})
-      CU(cudaEventCreate(pe));
-  // twiddles (br_core.cuh): ta[r][k0] = e^{i pi r(1-4k0)/1024}, tb[j][x] = e^{-2 pi i jx/64}
-  std::vector<cplx> ta(64 * 8), tb(8 * 8);
-  for (int r = 0; r < 64; r++)
-    for (int k0 = 0; k0 < 8; k0++) {
-      int idx = ((r * (1 - 4 * k0)) % 2048 + 2048) % 2048;
-      double ang = M_PI * (double)idx / 1024.0;
-      ta[r * 8 + k0] = br::mk(std::cos(ang), std::sin(ang));
-    }
-  for (int j = 0; j < 8; j++)
-    for (int x = 0; x < 8; x++) {
-      double ang = -2.0 * M_PI * (double)((j * x) % 64) / 64.0;
-      tb[j * 8 + x] = br::mk(std::cos(ang), std::sin(ang));
-    }
-  CU(cudaMalloc(reinterpret_cast<void **>(&e->tw_a), ta.size() * sizeof(cplx)));
-  CU(cudaMalloc(reinterpret_cast<void **>(&e->tw_b), tb.size() * sizeof(cplx)));
-  CU(cudaMemcpy(e->tw_a, ta.data(), ta.size() * sizeof(cplx), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(e->tw_b, tb.data(), tb.size() * sizeof(cplx), cudaMemcpyHostToDevice));
-  blob_layout(e);
+  int rc = engine_init(e, device_id);
+  if (rc != TFHE_OK) {  // release whatever was created; keep the error text
+    char saved[sizeof(g_err)];
+    memcpy(saved, g_err, sizeof(saved));
+    tfhe_engine_destroy(e);
+    memcpy(g_err, saved, sizeof(saved));
+    return rc;
+  }
   *out = e;
   return TFHE_OK;
 }
@@ -672,14 +685,23 @@ int tfhe_reenc_key_load(tfhe_engine *e, const uint32_t *key_encryptions, uint32_
   k->basebit = basebit; k->t = t; k->n_rows = base * t * e->p.n; k->dev = e->dev;
   const size_t src_bytes = (size_t)k->n_rows * (e->p.n + 1) * 4;
   const size_t dst_bytes = ((size_t)k->n_rows + 1) * e->ksk_stride * 4;
-  CU(cudaMalloc(reinterpret_cast<void **>(&k->rows), dst_bytes));
-  CU(e->s_misc.reserve(src_bytes));
-  CU(cudaMemcpyAsync(e->s_misc.p, key_encryptions, src_bytes, cudaMemcpyHostToDevice, e->stream));
-  CU(ksk_relayout_launch(static_cast<const uint32_t *>(e->s_misc.p), k->rows, k->n_rows, e->p.n,
-                         e->ksk_stride, e->stream));
-  e->launches++;
-  CU(cudaStreamSynchronize(e->stream));
+  auto upload = [&]() -> int {
+    CU(cudaMalloc(reinterpret_cast<void **>(&k->rows), dst_bytes));
+    CU(e->s_misc.reserve(src_bytes));
+    CU(cudaMemcpyAsync(e->s_misc.p, key_encryptions, src_bytes, cudaMemcpyHostToDevice, e->stream));
+    CU(ksk_relayout_launch(static_cast<const uint32_t *>(e->s_misc.p), k->rows, k->n_rows, e->p.n,
+                           e->ksk_stride, e->stream));
+    e->launches++;
+    CU(cudaStreamSynchronize(e->stream));
+    return TFHE_OK;
+  };
+  int rc = upload();
   e->s_misc.release();
+  if (rc != TFHE_OK) {
+    if (k->rows) cudaFree(k->rows);
+    delete k;
+    return rc;
+  }
   *out = k;
   return TFHE_OK;
 }

@@ -36,6 +36,17 @@ extern "C" {
     fn tfhe_lut_generate(e: *mut TfheEngine, f_table: *const u32, modulus: u32, scale: c_double,
         lut_b_out: *mut u32, lut_id_out: *mut c_int) -> c_int;
     fn tfhe_batch_bootstrap_lut(e: *mut TfheEngine, lut_id: c_int, input: *const u32, out: *mut u32, count: usize) -> c_int;
+    fn tfhe_batch_bootstrap_lut_multi(e: *mut TfheEngine, lut_ids: *const i32, input: *const u32, out: *mut u32, count: usize) -> c_int;
+    // key.rs:59-66 on the device; key blob checkpointing; proxy_reenc.rs:468-511
+    fn tfhe_engine_generate_cloud_key(e: *mut TfheEngine, s0: *const u32, s1: *const u32,
+        alpha_lv0: c_double, alpha_lv1: c_double, seed: u64) -> c_int;
+    fn tfhe_engine_cloud_key_export_bytes(e: *mut TfheEngine) -> usize;
+    fn tfhe_engine_export_cloud_key(e: *mut TfheEngine, buf: *mut c_void, bytes: usize) -> c_int;
+    fn tfhe_engine_import_cloud_key(e: *mut TfheEngine, buf: *const c_void, bytes: usize) -> c_int;
+    fn tfhe_reenc_key_load(e: *mut TfheEngine, key_encryptions: *const u32, base: u32, t: u32,
+        out: *mut *mut c_void) -> c_int;
+    fn tfhe_reenc_key_destroy(k: *mut c_void);
+    fn tfhe_batch_reencrypt(e: *mut TfheEngine, key: *const c_void, input: *const u32, out: *mut u32, count: usize) -> c_int;
 }
 
 #[derive(Copy, Clone)]
@@ -112,6 +123,28 @@ impl CudaBootstrap {
     }
 }
 
+impl CudaBootstrap {
+    /// CloudKey::new(&secret_key) (src/key.rs:59-66) generated on the GPU; the key never
+    /// exists in the reference layout on the host.
+    pub fn generate_cloud_key(&self, sk: &crate::key::SecretKey, seed: u64) {
+        check(unsafe { tfhe_engine_generate_cloud_key(self.raw, sk.key_lv0.as_ptr(), sk.key_lv1.as_ptr(),
+                                                      params::KSK_ALPHA, params::BSK_ALPHA, seed) });
+        *self.loaded_key.lock().unwrap() = usize::MAX; // device-resident key, not tied to a CloudKey
+    }
+
+    /// proxy_reenc::reencrypt_tlwe_lv0 (src/proxy_reenc.rs:468-511) over a batch.
+    pub fn batch_reencrypt(&self, key: &crate::proxy_reenc::ProxyReencryptionKey, cts: &[Ciphertext]) -> Vec<Ciphertext> {
+        let mut h: *mut c_void = std::ptr::null_mut();
+        check(unsafe { tfhe_reenc_key_load(self.raw, key.key_encryptions.as_ptr() as *const u32,
+                                           key.base as u32, key.t as u32, &mut h) });
+        let mut out = vec![Ciphertext::new(); cts.len()];
+        check(unsafe { tfhe_batch_reencrypt(self.raw, h, cts.as_ptr() as *const u32,
+                                            out.as_mut_ptr() as *mut u32, cts.len()) });
+        unsafe { tfhe_reenc_key_destroy(h) };
+        out
+    }
+}
+
 impl Drop for CudaBootstrap {
     fn drop(&mut self) { unsafe { tfhe_engine_destroy(self.raw) } }
 }
@@ -138,5 +171,3 @@ pub fn default_engine() -> &'static CudaBootstrap {
     static ENGINE: std::sync::OnceLock<CudaBootstrap> = std::sync::OnceLock::new();
     ENGINE.get_or_init(|| CudaBootstrap::new(0))
 }
-#[allow(dead_code)]
-fn _unused(_: *mut c_void) {}
