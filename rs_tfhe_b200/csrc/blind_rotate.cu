@@ -638,11 +638,9 @@ cudaError_t launch_v4(const BrArgs &args, int num_sms, cudaStream_t stream) {
   constexpr int G = 6, STAGES = 3;
   auto kern = blind_rotate_kernel_v4<L, BGBIT>;
   const int smem = STAGES * kStageBytes + G * Cfg<L, 2>::kGroupBytes + 2 * STAGES * 8 + 16;
-  static bool configured = false;
-  if (!configured) {
+  {  // per device and cheap: set on every launch (engines may live on several GPUs)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   int grid = (int)(args.count < (size_t)num_sms ? args.count : (size_t)num_sms);
   if (grid < 1) grid = 1;
@@ -876,11 +874,9 @@ template <int L, int BGBIT>
 cudaError_t launch_latency(const BrArgs &args, int num_sms, cudaStream_t stream) {
   auto kern = blind_rotate_latency_kernel<L, BGBIT>;
   const int smem = 2 * L * kStageBytes + 2 * kN * 4 + L * 2 * kExchStride * 16 + 2432 + 4 * L * 8 + 16;
-  static bool configured = false;
-  if (!configured) {
+  {  // per device and cheap: set on every launch (engines may live on several GPUs)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   int grid = (int)(args.count < (size_t)num_sms ? args.count : (size_t)num_sms);
   if (grid < 1) grid = 1;
@@ -892,11 +888,9 @@ template <int L, int BGBIT, int G, int STAGES, int NBUF, bool TMEM_TW, int RC, i
 cudaError_t launch_v(const BrArgs &args, int num_sms, cudaStream_t stream) {
   auto kern = blind_rotate_kernel<L, BGBIT, G, STAGES, NBUF, TMEM_TW, RC, RP, PARK>;
   const int smem = STAGES * kStageBytes + G * Cfg<L, NBUF>::kGroupBytes + 2 * STAGES * 8 + 16;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
+  {  // per device and cheap: set on every launch (engines may live on several GPUs)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   int grid = (int)(args.count < (size_t)num_sms ? args.count : (size_t)num_sms);
   if (grid < 1) grid = 1;

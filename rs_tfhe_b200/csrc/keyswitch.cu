@@ -145,12 +145,10 @@ __global__ void __launch_bounds__(192) keyswitch_base4_kernel(const KsArgs a) {
 
 template <int T> cudaError_t launch_base4(const KsArgs &args, cudaStream_t stream) {
   const int smem = KS4_B * br::kN * 4;
-  static bool configured = false;
-  if (!configured) {
+  {  // per device and cheap: set on every launch (engines may live on several GPUs)
     cudaError_t e = cudaFuncSetAttribute(keyswitch_base4_kernel<T>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   const uint32_t stride4 = args.stride >> 2;
   const int threads = (int)((stride4 + 31) & ~31u);

@@ -185,11 +185,9 @@ cudaError_t ks_mma_launch(const KsMmaArgs &args, cudaStream_t stream) {
   const size_t mtiles = (args.count + KM_MT * 16 - 1) / (KM_MT * 16);
   const unsigned grid = (unsigned)(mtiles * (args.nxg / KM_WARPS));
   const int smem = KM_DEPTH * 2 * KM_WARPS * 32 * 16;
-  static bool configured = false;
-  if (!configured) {
+  {  // per device and cheap: set on every launch (engines may live on several GPUs)
     cudaError_t e = cudaFuncSetAttribute(ks_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   ks_mma_kernel<<<grid, KM_WARPS * 32, smem, stream>>>(args);
   return cudaGetLastError();
