@@ -190,8 +190,9 @@ template <int L, int NBUF> struct Cfg {
 //       TMEM, pass-B twiddles rebuilt from three base values     (consumers 160 regs)
 template <int L, int BGBIT, int G, int STAGES, int NBUF, bool TMEM_TW, int REGS_CONS, int REGS_PROD,
           bool PARK = false>
-__global__ void __launch_bounds__(G * 64 + 128, 1) blind_rotate_kernel(const BrArgs args) {
+__global__ void __launch_bounds__(((2 * G + 3) / 4) * 128 + 128, 1) blind_rotate_kernel(const BrArgs args) {
   using C = Cfg<L, NBUF>;
+  constexpr int PW = ((2 * G + 3) / 4) * 4;  // first producer warp: its own warpgroup
   constexpr int L2 = 2 * L;
   constexpr bool EXACT = (L == 3 && BGBIT == 6);
   static_assert(NBUF >= 2 && (L <= NBUF || (L == 3 && NBUF == 2)), "unsupported buffer plan");
@@ -229,10 +230,10 @@ __global__ void __launch_bounds__(G * 64 + 128, 1) blind_rotate_kernel(const BrA
   // Register budget: the SM sub-partition hosting the producer warpgroup also hosts
   // consumer warps, so the launch is compiled at 65536/blockDim registers/thread and
   // rebalanced here (SASS: USETMAXREG).
-  if (warp >= 2 * G) {
+  if (warp >= PW) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PROD));
     // ===== producer: stream BSK rows (i, r) for every round =====
-    if (warp == 2 * G && lane == 0) {
+    if (warp == PW && lane == 0) {
       const uint8_t *src0 = reinterpret_cast<const uint8_t *>(args.bsk);
       uint32_t stage = 0, parity = 0;
       const uint32_t rows = n * L2;
@@ -251,6 +252,7 @@ __global__ void __launch_bounds__(G * 64 + 128, 1) blind_rotate_kernel(const BrA
 
   // ===== consumers: group g owns one ciphertext per round =====
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_CONS));
+  if (warp >= 2 * G) return;  // padding warps of a partially filled consumer warpgroup (odd G)
   const int g = warp >> 1;
   const int tid = threadIdx.x & 63;
   uint8_t *gbase = groups + g * C::kGroupBytes;
@@ -894,7 +896,7 @@ cudaError_t launch_v(const BrArgs &args, int num_sms, cudaStream_t stream) {
   }
   int grid = (int)(args.count < (size_t)num_sms ? args.count : (size_t)num_sms);
   if (grid < 1) grid = 1;
-  kern<<<grid, G * 64 + 128, smem, stream>>>(args);
+  kern<<<grid, ((2 * G + 3) / 4) * 128 + 128, smem, stream>>>(args);
   return cudaGetLastError();
 }
 
@@ -903,7 +905,7 @@ int br_variant() {
   if (v < 0) {
     const char *e = getenv("TFHE_BR_VARIANT");
     v = e ? atoi(e) : BR_DEFAULT_VARIANT;
-    if (v < 1 || v > 5) v = BR_DEFAULT_VARIANT;
+    if (v < 1 || v > 6) v = BR_DEFAULT_VARIANT;
   }
   return v;
 }
@@ -923,6 +925,8 @@ cudaError_t launch_t(const BrArgs &args, int num_sms, cudaStream_t stream) {
   if (L > 1 && args.count <= (size_t)br_latency_threshold(num_sms))
     return launch_latency<L, BGBIT>(args, num_sms, stream);
   if (br_variant() == 4) return launch_v4<L, BGBIT>(args, num_sms, stream);
+  if (br_variant() == 6)  // five groups per SM at 160 registers (3 exchange buffers, 2-stage ring)
+    return launch_v<L, BGBIT, 5, 2, 3, true, 160, 24, true>(args, num_sms, stream);
   if (br_variant() == 5)  // variant 3 + MAC accumulators parked in TMEM across poly b's passes A/B
     return launch_v<L, BGBIT, 4, 4, 3, true, 232, 40, true>(args, num_sms, stream);
   if (br_variant() == 2)

@@ -1,5 +1,5 @@
 """Every selectable kernel variant stays bit-exact: the experimental blind-rotation variants
-(TFHE_BR_VARIANT=1..5 with the small-batch latency kernel disabled; 3 is the default
+(TFHE_BR_VARIANT=1..6 with the small-batch latency kernel disabled; 3 is the default
 throughput variant, and TFHE_BR_LATENCY_MAX selects up to which batch size the latency kernel runs) and the row-walk key switch (TFHE_KS_VARIANT=rows,
 TFHE_KS_GENERIC=1) run tools/sanitize.py -- mixed gates, LUT bootstrap, blind rotate +
 extract/key switch, each compared word for word with the oracle -- in their own process
@@ -17,7 +17,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.mark.parametrize("env", [
     {"TFHE_BR_VARIANT": "1", "TFHE_BR_LATENCY_MAX": "0"}, {"TFHE_BR_VARIANT": "2", "TFHE_BR_LATENCY_MAX": "0"},
     {"TFHE_BR_VARIANT": "3", "TFHE_BR_LATENCY_MAX": "0"}, {"TFHE_BR_VARIANT": "4", "TFHE_BR_LATENCY_MAX": "0"},
-    {"TFHE_BR_VARIANT": "5", "TFHE_BR_LATENCY_MAX": "0"}, {"TFHE_BR_LATENCY_MAX": "1000"},
+    {"TFHE_BR_VARIANT": "5", "TFHE_BR_LATENCY_MAX": "0"}, {"TFHE_BR_VARIANT": "6", "TFHE_BR_LATENCY_MAX": "0"},
+    {"TFHE_BR_LATENCY_MAX": "1000"},
     {"TFHE_KS_VARIANT": "rows"}, {"TFHE_KS_VARIANT": "rows", "TFHE_KS_GENERIC": "1"},
 ], ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
 def test_variant_bit_exact(env):
