@@ -20,6 +20,20 @@ __global__ void bsk_relayout_kernel(const double *__restrict__ src, cplx *__rest
   dst[idx] = br::mk(s[k] * (1.0 / 1024.0), s[k + br::kHalf] * (1.0 / 1024.0));
 }
 
+// Device-order key rows -> the thread order of the TMEM-exchange kernel (blind_rotate.cu): slot
+// T = 32 W + l of a (k2, o) slice holds bin k0 + 8 k1 + 64 k2 with k0 = 4 W + l[3:2],
+// k1 = 4 l[4] + l[1:0], negated where k2 is odd and l[4] is set (the kernel's pass C produces those
+// bins negated); the standard order keeps that bin in slot 8 k0 + k1.
+__global__ void bsk_permute_kernel(const cplx *__restrict__ src, cplx *__restrict__ dst, size_t total) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int T = idx & 63;
+  const int k0 = 4 * (T >> 5) + ((T >> 2) & 3), k1 = 4 * ((T >> 4) & 1) + (T & 3);
+  const cplx v = src[(idx & ~(size_t)63) + 8 * k0 + k1];
+  const bool neg = ((idx >> 7) & 1) && ((T >> 4) & 1);   // idx = ((row * 8 + k2) * 2 + o) * 64 + T
+  dst[idx] = neg ? br::mk(-v.x, -v.y) : v;
+}
+
 // Reference KSK image (key.rs:102-122: u32[N*t*2^basebit][n+1]) -> rows padded to
 // `stride` words (zero fill) plus one trailing all-zero row.
 __global__ void ksk_relayout_kernel(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst,
@@ -103,6 +117,12 @@ cudaError_t bsk_relayout_launch(const double *src_ref, cplx *dst, uint32_t n, ui
   bsk_relayout_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src_ref, dst, total);
   return cudaGetLastError();
 }
+cudaError_t bsk_permute_launch(const cplx *src, cplx *dst, size_t rows, cudaStream_t stream) {
+  const size_t total = rows * br::kChunkCplx;
+  bsk_permute_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src, dst, total);
+  return cudaGetLastError();
+}
+
 cudaError_t ksk_relayout_launch(const uint32_t *src_ref, uint32_t *dst, uint32_t rows, uint32_t n,
                                 uint32_t stride, cudaStream_t stream) {
   size_t total = ((size_t)rows + 1) * stride;

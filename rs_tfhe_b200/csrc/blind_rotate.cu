@@ -85,6 +85,9 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
 __device__ __forceinline__ void group_sync(int g) {
   asm volatile("bar.sync %0, 64;" ::"r"(g + 1) : "memory");
 }
+template <int THREADS> __device__ __forceinline__ void group_sync_n(int g) {
+  asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(THREADS) : "memory");
+}
 
 // gates.rs:54-150: out = ca*a + cb*b, b-word += off
 __constant__ int32_t c_gate_ca[TFHE_GATE_COUNT] = {-1, 1, 1, 1, 1, -1, -1, 1, -1, 1};
@@ -188,11 +191,24 @@ template <int L, int NBUF> struct Cfg {
 //   V1: G=4 groups, 3 exchange buffers, twiddles in registers   (consumers 232 regs)
 //   V2: G=6 groups, 2 exchange buffers (digits in sub-rounds of <=2), pass-A twiddles in
 //       TMEM, pass-B twiddles rebuilt from three base values     (consumers 160 regs)
+//   CPW ("ciphertexts per warp", 1/2/4): a warp carries 32/CPW lanes of each of CPW ciphertexts
+//       that sit at the same ring position, so the lanes of different ciphertexts read the SAME
+//       key words in the MAC and shared memory serves them as one broadcast wavefront.
+//   MAGIC: int<->double conversions of the exact regime as 2^52-biased bit patterns + one DADD
+//       (FP64 pipe) instead of I2F/F2I (quarter-rate conversion pipe).
 template <int L, int BGBIT, int G, int STAGES, int NBUF, bool TMEM_TW, int REGS_CONS, int REGS_PROD,
-          bool PARK = false>
-__global__ void __launch_bounds__(((2 * G + 3) / 4) * 128 + 128, 1) blind_rotate_kernel(const BrArgs args) {
+          bool PARK = false, int CPW = 1, bool MAGIC = false, bool SPLIT = true>
+__global__ void __launch_bounds__(SPLIT ? ((2 * G + 3) / 4) * 128 + 128 : 2 * G * 32 + 32, 1)
+    blind_rotate_kernel(const BrArgs args) {
+  static_assert(CPW == 1 || (G % CPW == 0 && (CPW == 2 || CPW == 4)), "CPW must divide G");
+  static_assert(!MAGIC || (L == 3 && BGBIT == 6), "MAGIC conversions need the exact regime");
+  constexpr int LPC = 32 / CPW;        // lanes per ciphertext in a warp
+  constexpr int GT = 64 * CPW;         // threads that share group barriers
+  constexpr int kPad = CPW > 1 ? 128 / CPW : 0;  // bank rotation between the ciphertexts of a warp
   using C = Cfg<L, NBUF>;
-  constexpr int PW = ((2 * G + 3) / 4) * 4;  // first producer warp: its own warpgroup
+  // SPLIT: producer in its own warpgroup, registers rebalanced with setmaxnreg; !SPLIT: one extra
+  // warp after the consumers, every warp keeps the launch-time register count (65536/blockDim)
+  constexpr int PW = SPLIT ? ((2 * G + 3) / 4) * 4 : 2 * G;
   constexpr int L2 = 2 * L;
   constexpr bool EXACT = (L == 3 && BGBIT == 6);
   static_assert(NBUF >= 2 && (L <= NBUF || (L == 3 && NBUF == 2)), "unsupported buffer plan");
@@ -201,7 +217,7 @@ __global__ void __launch_bounds__(((2 * G + 3) / 4) * 128 + 128, 1) blind_rotate
   extern __shared__ __align__(128) uint8_t smem[];
   cplx *ring = reinterpret_cast<cplx *>(smem);
   uint8_t *groups = smem + STAGES * kStageBytes;
-  uint64_t *full = reinterpret_cast<uint64_t *>(groups + G * C::kGroupBytes);
+  uint64_t *full = reinterpret_cast<uint64_t *>(groups + G * C::kGroupBytes + 128);
   uint64_t *empty = full + STAGES;
   uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(empty + STAGES);
 
@@ -231,7 +247,7 @@ __global__ void __launch_bounds__(((2 * G + 3) / 4) * 128 + 128, 1) blind_rotate
   // consumer warps, so the launch is compiled at 65536/blockDim registers/thread and
   // rebalanced here (SASS: USETMAXREG).
   if (warp >= PW) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PROD));
+    if constexpr (SPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PROD));
     // ===== producer: stream BSK rows (i, r) for every round =====
     if (warp == PW && lane == 0) {
       const uint8_t *src0 = reinterpret_cast<const uint8_t *>(args.bsk);
@@ -251,11 +267,13 @@ __global__ void __launch_bounds__(((2 * G + 3) / 4) * 128 + 128, 1) blind_rotate
   }
 
   // ===== consumers: group g owns one ciphertext per round =====
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_CONS));
+  if constexpr (SPLIT) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_CONS));
   if (warp >= 2 * G) return;  // padding warps of a partially filled consumer warpgroup (odd G)
-  const int g = warp >> 1;
-  const int tid = threadIdx.x & 63;
-  uint8_t *gbase = groups + g * C::kGroupBytes;
+  const int gg = warp / (2 * CPW);                       // barrier group (CPW ciphertexts)
+  const int q = lane / LPC;                              // which of the warp's ciphertexts
+  const int g = gg * CPW + q;                            // ciphertext slot in the CTA
+  const int tid = (warp % (2 * CPW)) * LPC + (lane % LPC);
+  uint8_t *gbase = groups + g * C::kGroupBytes + q * kPad;
   uint32_t *acc = reinterpret_cast<uint32_t *>(gbase);
   cplx *exch = reinterpret_cast<cplx *>(gbase + C::kAccBytes);
   uint16_t *abar_s = reinterpret_cast<uint16_t *>(gbase + C::kAccBytes + C::kExchBytes);
@@ -326,10 +344,13 @@ __global__ void __launch_bounds__(((2 * G + 3) / 4) * 128 + 128, 1) blind_rotate
       for (int x = tid; x < 2 * kN; x += 64)
         acc[x] = rot_coeff(tv + (x & ~(kN - 1)), x & (kN - 1), b_tilda);
     }
-    group_sync(g);
+    group_sync_n<GT>(gg);
 
+    // with CPW > 1 the lanes of an idle tail ciphertext ride along on whatever its buffers hold
+    // (every u32 is a valid torus word); only their loads and stores are masked
+    const bool warp_active = CPW == 1 ? active : (__ballot_sync(0xffffffffu, active) != 0u);
     for (uint32_t i = 0; i < n; i++) {
-      if (active) {
+      if (warp_active) {
         cplx racc[2][8];
         const uint32_t abar = abar_s[i];
 #pragma unroll
@@ -342,14 +363,14 @@ __global__ void __launch_bounds__(((2 * G + 3) / 4) * 128 + 128, 1) blind_rotate
           load_t(tid, acc + p * kN, abar, args.offset, t_re, t_im);
           {
             BR_GET_TA(ta)
-            fwd_pass_a<BGBIT, 0, ND0>(tid, t_re, t_im, ta, exch);
+            fwd_pass_a<BGBIT, 0, ND0, MAGIC>(tid, t_re, t_im, ta, exch);
           }
-          group_sync(g);
+          group_sync_n<GT>(gg);
           {
             BR_GET_TB(tb)
             fwd_pass_b<ND0>(tid, tb, exch);
           }
-          group_sync(g);
+          group_sync_n<GT>(gg);
           if (PARK && p == 1) {   // accumulators were parked in TMEM during poly b's passes A/B
             unpark8(taddr + 32, racc[0]);
             unpark8(taddr + 64, racc[1]);
@@ -360,34 +381,34 @@ __global__ void __launch_bounds__(((2 * G + 3) / 4) * 128 + 128, 1) blind_rotate
             park8(taddr + 64, racc[1]);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           }
-          group_sync(g);
+          group_sync_n<GT>(gg);
           if constexpr (ND1 > 0) {
             {
               BR_GET_TA(ta)
-              fwd_pass_a<BGBIT, ND0, ND1>(tid, t_re, t_im, ta, exch);
+              fwd_pass_a<BGBIT, ND0, ND1, MAGIC>(tid, t_re, t_im, ta, exch);
             }
-            group_sync(g);
+            group_sync_n<GT>(gg);
             {
               BR_GET_TB(tb)
               fwd_pass_b<ND1>(tid, tb, exch);
             }
-            group_sync(g);
+            group_sync_n<GT>(gg);
             BR_MAC_DIGITS(ND1)
-            group_sync(g);
+            group_sync_n<GT>(gg);
           }
         }
         {
           BR_GET_TB(tb)
           inv_pass_c(tid, tb, racc, exch);
         }
-        group_sync(g);
+        group_sync_n<GT>(gg);
         inv_pass_b(tid, exch);
-        group_sync(g);
+        group_sync_n<GT>(gg);
         {
           BR_GET_TA(ta)
-          inv_pass_a<EXACT>(tid, ta, exch, acc);
+          inv_pass_a<EXACT, MAGIC>(tid, ta, exch, acc);
         }
-        group_sync(g);
+        group_sync_n<GT>(gg);
       } else {
         // idle group: keep the ring's phase accounting in lock step
         for (int c = 0; c < L2; c++) {
@@ -416,7 +437,7 @@ __global__ void __launch_bounds__(((2 * G + 3) / 4) * 128 + 128, 1) blind_rotate
         }
       }
     }
-    group_sync(g);
+    group_sync_n<GT>(gg);
   }
 #undef BR_GET_TA
 #undef BR_GET_TB
@@ -426,6 +447,644 @@ __global__ void __launch_bounds__(((2 * G + 3) / 4) * 128 + 128, 1) blind_rotate
     if (warp == 0)
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(*tmem_base_s));
   }
+}
+
+// ---- TMEM-staged key rows ----------------------------------------------------------------------
+// In the kernel above every group re-reads each staged key row from shared memory (4 x 16 KB per
+// row: a quarter of all shared-memory wavefronts, and the MAC phase is the most shared-memory-
+// bound one).  Here a row goes global -> shared (TMA, as before) -> TENSOR MEMORY with
+// tcgen05.cp 64x128b.warpx2::02_13: one copy instruction moves the 64 x 16 B slice of one
+// (k2, o) pair and multicasts rows 0-31 to lane quadrants 0 and 2, rows 32-63 to quadrants 1 and
+// 3 -- exactly the TMEM lanes of the even / odd warps of every group -- so each consumer thread
+// finds its 16 key words of the row in 64 consecutive columns of its own TMEM lane and reads
+// them with tcgen05.ld (12-cycle latency, own data path).  Shared memory is read once per row
+// instead of four times; the shared ring shrinks to SSTAGES slots and the TMEM ring holds TSTAGES
+// rows, so groups can drift a whole step apart.
+//   warp PW   lane 0: TMA producer   (waits empty[s]  <- tcgen05.commit of the copies that read slot s)
+//   warp PW+1 lane 0: copy issuer    (waits full[s], tempty[t]; 16 x tcgen05.cp; commits -> empty[s], tfull[t])
+//   consumers       : wait tfull[t]; tcgen05.ld; MAC; arrive tempty[t]
+__device__ __forceinline__ uint64_t smem_desc_noswizzle(uint32_t saddr) {
+  // K-major, SWIZZLE_NONE: 8-row x 16 B core matrices, 128 B apart in both directions; version 1
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) |
+         ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// completion of every outstanding tcgen05.ld of this thread; the loaded registers are threaded
+// through as in/out operands so no use can be scheduled above the wait
+__device__ __forceinline__ void tmem_wait_ld16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ cplx cplx_from_words(const uint32_t *w) {
+  return mk(__hiloint2double((int)w[1], (int)w[0]), __hiloint2double((int)w[3], (int)w[2]));
+}
+// pass C + MAC with the key row in TMEM: columns [(k2*2+o)*4, +4) of this thread's lane
+__device__ __forceinline__ void fwd_pass_c_mac_tmem(int tid, const cplx *exch_d, uint32_t trow, cplx (&acc)[2][8]) {
+  const cplx *e = exch_d + tid * 9;
+  cplx v[8];
+#pragma unroll
+  for (int j0 = 0; j0 < 8; j0++) v[j0] = e[j0];
+  uint32_t b0[16], b1[16];
+  tmem_ld16(trow, b0);
+  dft8<false>(v);
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    if (c & 1) tmem_wait_ld16(b1); else tmem_wait_ld16(b0);
+    if (c < 3) { if (c & 1) tmem_ld16(trow + 16 * (c + 1), b0); else tmem_ld16(trow + 16 * (c + 1), b1); }
+    const uint32_t *b = (c & 1) ? b1 : b0;
+#pragma unroll
+    for (int kk = 0; kk < 2; kk++) {
+      cfma(acc[0][2 * c + kk], v[2 * c + kk], cplx_from_words(b + kk * 8));
+      cfma(acc[1][2 * c + kk], v[2 * c + kk], cplx_from_words(b + kk * 8 + 4));
+    }
+  }
+}
+
+template <int L, int BGBIT, int SSTAGES, int TSTAGES, bool MAGIC, int EXP = 0>
+__global__ void __launch_bounds__(384, 1) blind_rotate_kernel_t(const BrArgs args) {
+  constexpr int G = 4, NBUF = 3, PW = 8, L2 = 2 * L;
+  using C = Cfg<L, NBUF>;
+  constexpr bool EXACT = (L == 3 && BGBIT == 6);
+  static_assert(L <= NBUF, "one sub-round per polynomial");
+  static_assert(64 + TSTAGES * 64 <= 512, "TMEM columns");
+  constexpr uint32_t kKeyCol0 = 64;   // TMEM columns [0,64): pass-A twiddles; then TSTAGES rows of 64 columns
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t *ring = smem;
+  uint8_t *groups = smem + SSTAGES * kStageBytes;
+  uint64_t *full = reinterpret_cast<uint64_t *>(groups + G * C::kGroupBytes);
+  uint64_t *empty = full + SSTAGES;
+  uint64_t *tfull = empty + SSTAGES;
+  uint64_t *tempty = tfull + TSTAGES;
+  uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(tempty + TSTAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t n = args.n;
+  const uint32_t grid = gridDim.x;
+  const uint32_t per_round = grid * G;
+  const uint32_t rounds = (uint32_t)((args.count + per_round - 1) / per_round);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SSTAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int t = 0; t < TSTAGES; t++) { mbar_init(&tfull[t], 1); mbar_init(&tempty[t], 2 * G); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
+        smem_u32(tmem_base_s)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tbase = *tmem_base_s;
+
+  if (warp >= PW) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    const uint32_t rows = n * L2;
+    if (warp == PW && lane == 0) {
+      // ===== TMA producer: key rows global -> shared ring =====
+      const uint8_t *src0 = reinterpret_cast<const uint8_t *>(args.bsk);
+      uint32_t stage = 0, parity = 0;
+      for (uint32_t rd = 0; rd < rounds; rd++)
+        for (uint32_t row = 0; row < rows; row++) {
+          mbar_wait_backoff(&empty[stage], parity ^ 1);
+          mbar_arrive_expect_tx(&full[stage], kStageBytes);
+          tma_load_1d(ring + stage * kStageBytes, src0 + (size_t)row * kStageBytes, kStageBytes, &full[stage]);
+          if (++stage == SSTAGES) { stage = 0; parity ^= 1; }
+        }
+    } else if (warp == PW + 1 && lane == 0) {
+      // ===== copy issuer: shared ring -> TMEM ring (SASS: UTCCP) =====
+      uint32_t stage = 0, parity = 0, ts = 0, tparity = 0;
+      for (uint32_t rd = 0; rd < rounds; rd++)
+        for (uint32_t row = 0; row < rows; row++) {
+          mbar_wait_backoff(&tempty[ts], tparity ^ 1);
+          mbar_wait_backoff(&full[stage], parity);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t src = smem_u32(ring + stage * kStageBytes);
+          const uint32_t dst = tbase + kKeyCol0 + ts * 64;
+#pragma unroll
+          for (int sl = 0; sl < (EXP == 2 ? 0 : 16); sl++)   // EXP 2 (timing experiment, wrong results): no copies
+            asm volatile("tcgen05.cp.cta_group::1.64x128b.warpx2::02_13 [%0], %1;" ::"r"(dst + 4 * sl),
+                         "l"(smem_desc_noswizzle(src + sl * 1024))
+                         : "memory");
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                           smem_u32(&empty[stage]))
+                       : "memory");
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                           smem_u32(&tfull[ts]))
+                       : "memory");
+          if (++stage == SSTAGES) { stage = 0; parity ^= 1; }
+          if (++ts == TSTAGES) { ts = 0; tparity ^= 1; }
+        }
+    }
+    return;
+  }
+
+  // ===== consumers: group g owns one ciphertext per round =====
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+  const int g = warp >> 1;
+  const int tid = threadIdx.x & 63;
+  uint8_t *gbase = groups + g * C::kGroupBytes;
+  uint32_t *acc = reinterpret_cast<uint32_t *>(gbase);
+  cplx *exch = reinterpret_cast<cplx *>(gbase + C::kAccBytes);
+  uint16_t *abar_s = reinterpret_cast<uint16_t *>(gbase + C::kAccBytes + C::kExchBytes);
+
+  const uint32_t tlane = tbase + (((uint32_t)(warp & 3) * 32u) << 16);
+  const uint32_t taddr = tlane + (uint32_t)(warp >> 2) * 32u;
+  cplx tb1, tb2, tb4;
+  {
+    const cplx *twb = args.tw_b + (tid & 7) * 8;
+    tb1 = twb[1]; tb2 = twb[2]; tb4 = twb[4];
+    cplx ta[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) ta[k] = args.tw_a[tid * 8 + k];
+    tmem_st_ta(taddr, ta);
+  }
+
+  const uint32_t w = n + 1;
+  uint32_t ts = 0, tparity = 0;
+
+  for (uint32_t rd = 0; rd < rounds; rd++) {
+    const size_t ct = ((size_t)rd * G + g) * grid + blockIdx.x;
+    const bool active = ct < args.count;
+
+    if (active) {
+      // ---- K0: linear pre-combination + modulus switch (trgsw.rs:202-203, 210-211)
+      uint32_t ca = 1, cb = 0, off = 0;
+      const uint32_t *A, *B;
+      if (args.op >= 0 || args.ops) {
+        int op = args.ops ? (int)args.ops[ct] : args.op;
+        ca = (uint32_t)c_gate_ca[op]; cb = (uint32_t)c_gate_cb[op]; off = c_gate_off[op];
+        A = args.in + ct * 2 * w;
+        B = A + w;
+      } else {
+        A = args.in + ct * w;
+        B = A;
+      }
+      for (uint32_t i = tid; i < n; i += 64) {
+        uint32_t v = ca * A[i] + cb * B[i];
+        abar_s[i] = (uint16_t)((uint32_t)(v + (1u << 20)) >> 21);
+      }
+      uint32_t bw = ca * A[n] + cb * B[n] + off;
+      uint32_t b_tilda = (uint32_t)(2 * kN - (((uint64_t)bw + (1u << 20)) >> 21));
+      const int tvi = args.tv_index ? args.tv_index[ct] : args.tv_default;
+      const uint32_t *tv = args.tv + (size_t)tvi * 2 * kN;
+      for (int x = tid; x < 2 * kN; x += 64)
+        acc[x] = rot_coeff(tv + (x & ~(kN - 1)), x & (kN - 1), b_tilda);
+    }
+    group_sync(g);
+
+    for (uint32_t i = 0; i < n; i++) {
+      if (active) {
+        cplx racc[2][8];
+        const uint32_t abar = abar_s[i];
+#pragma unroll
+        for (int o = 0; o < 2; o++)
+#pragma unroll
+          for (int k = 0; k < 8; k++) racc[o][k] = mk(0.0, 0.0);
+#pragma unroll 1
+        for (int p = 0; p < 2; p++) {
+          uint32_t t_re[8], t_im[8];
+          load_t(tid, acc + p * kN, abar, args.offset, t_re, t_im);
+          {
+            cplx ta[8];
+            tmem_ld_ta(taddr, ta);
+            fwd_pass_a<BGBIT, 0, L, MAGIC>(tid, t_re, t_im, ta, exch);
+          }
+          group_sync(g);
+          {
+            cplx tb[8];
+            expand_tb(tb1, tb2, tb4, tb);
+            fwd_pass_b<L>(tid, tb, exch);
+          }
+          group_sync(g);
+#pragma unroll
+          for (int d = 0; d < L; d++) {
+            mbar_wait(&tfull[ts], tparity);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (EXP == 1)   // timing experiment (wrong results): copies run, consumers read the shared ring instead
+              fwd_pass_c_mac(tid, exch + d * kExchStride, reinterpret_cast<const cplx *>(ring) + (ts % SSTAGES) * kChunkCplx, racc);
+            else
+              fwd_pass_c_mac_tmem(tid, exch + d * kExchStride, tlane + kKeyCol0 + ts * 64, racc);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[ts]);
+            if (++ts == TSTAGES) { ts = 0; tparity ^= 1; }
+          }
+          group_sync(g);
+        }
+        {
+          cplx tb[8];
+          expand_tb(tb1, tb2, tb4, tb);
+          inv_pass_c(tid, tb, racc, exch);
+        }
+        group_sync(g);
+        inv_pass_b(tid, exch);
+        group_sync(g);
+        {
+          cplx ta[8];
+          tmem_ld_ta(taddr, ta);
+          inv_pass_a<EXACT, MAGIC>(tid, ta, exch, acc);
+        }
+        group_sync(g);
+      } else {
+        // idle group: keep the TMEM ring's phase accounting in lock step
+        for (int c = 0; c < L2; c++) {
+          mbar_wait(&tfull[ts], tparity);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[ts]);
+          if (++ts == TSTAGES) { ts = 0; tparity ^= 1; }
+        }
+      }
+    }
+
+    if (active) {
+      // ---- epilogue: TRLWE, or fused sample extraction (trlwe.rs:106-136)
+      if (args.out_mode == BR_OUT_TRLWE) {
+        uint32_t *o = args.out + ct * 2 * kN;
+        for (int x = tid; x < 2 * kN; x += 64) o[x] = acc[x];
+      } else {
+        const uint32_t m = args.out_mode == BR_OUT_EXTRACT ? (uint32_t)kN : n;
+        uint32_t *o = args.out + ct * (m + 1);
+        for (uint32_t x = tid; x <= m; x += 64) {
+          uint32_t v;
+          if (x == 0) v = acc[0];
+          else if (x == m) v = acc[kN];
+          else v = ~acc[m - x];
+          o[x] = v;
+        }
+      }
+    }
+    group_sync(g);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  asm volatile("bar.sync 15, %0;" ::"n"(G * 64) : "memory");  // all consumers done with TMEM
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tbase));
+}
+
+template <int L, int BGBIT, int SSTAGES, int TSTAGES, bool MAGIC_REQ, int EXP = 0>
+cudaError_t launch_tmem(const BrArgs &args, int num_sms, cudaStream_t stream) {
+  constexpr bool MAGIC = MAGIC_REQ && L == 3 && BGBIT == 6;
+  auto kern = blind_rotate_kernel_t<L, BGBIT, SSTAGES, TSTAGES, MAGIC, EXP>;
+  const int smem = SSTAGES * kStageBytes + 4 * Cfg<L, 3>::kGroupBytes + (2 * SSTAGES + 2 * TSTAGES) * 8 + 16;
+  {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+  }
+  int grid = (int)(args.count < (size_t)num_sms ? args.count : (size_t)num_sms);
+  if (grid < 1) grid = 1;
+  kern<<<grid, 384, smem, stream>>>(args);
+  return cudaGetLastError();
+}
+
+// ---- intra-warp FFT exchange through tensor memory ---------------------------------------------
+// The pass B -> C exchange (and C' -> B' in the inverse) swaps the 3 register-index bits with 3
+// lane bits of the SAME warp.  Instead of a padded shared-memory transpose + group barrier it runs as
+//   tcgen05.st.32x32b.x32  (thread = TMEM lane, register = column)
+//   tcgen05.ld.16x256b.x4  (twice: lanes 0-15 / 16-31)     -> swaps lane bits (4,3) with two
+//                                                              register bits, rotates lanes 2..0 up
+//   one shfl.xor 16 stage on half of the values             -> swaps the third bit
+// (inverse: shuffle stage, tcgen05.st.16x256b.x4 twice, tcgen05.ld.32x32b.x32).  Measured on B200
+// (tools/probe/tmem_xchg_probe.cu): the pair moves 8 KB per warp in ~29 cycles of throughput and
+// does not touch the shared-memory pipe, which is the kernel's tightest resource; it needs no
+// barrier because both directions stay inside one warp.  Which half a lane keeps and which it trades
+// depends on a lane bit; instead of selecting registers (48 selects per exchange) the choice is
+// absorbed into signs: dft8s (br_core.cuh) delivers its outputs with slots s and s^4 swapped for
+// sg = -1, an input swapped that way yields odd outputs negated, and those signs ride on the
+// permuted key (forward) and on the inverse pass-A twiddles (inverse).  tools/model/xchg_model.py
+// is the numpy model of this index/sign algebra.  Thread maps of a group (W = warp in group, l = lane):
+//   pass A / A' : T = j0 + 8 j1                              (unchanged; rows of the exchange buffer
+//                                                             are kS = 73 apart so pass B is bank-clean)
+//   pass B / B' : W = k0[2], l = (j0[1] j0[0] j0[2] k0[1] k0[0]),  registers j1 -> slot s = k1 ^ 4 l[2]
+//   pass C / C' : W = k0[2], l = (k1[2] k0[1] k0[0] k1[1] k1[0]),  registers: slot p = j0 ^ 4 l[4] -> k2
+// so bin k0 + 8 k1 + 64 k2 sits in thread T = 32 W + l, register k2, times (-1)^(k2 l[4]): the key is
+// permuted and signed to that order once at upload (bsk_permute_kernel, BrArgs::bsk2).
+constexpr int kS = 73;                    // exchange-buffer row pitch (complex) of this kernel
+constexpr int kXStride = 8 * kS;          // 584 complex per buffer
+
+__device__ __forceinline__ void tmem_st16x256_x4(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16x256_x4(uint32_t taddr, uint32_t (&a)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]),
+        "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld32(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cword(const cplx &c, int im, int hi) {
+  const double d = im ? c.y : c.x;
+  return (uint32_t)(hi ? __double2hiint(d) : __double2loint(d));
+}
+__device__ __forceinline__ cplx shfl16(const cplx &c) {
+  return mk(__shfl_xor_sync(0xffffffffu, c.x, 16), __shfl_xor_sync(0xffffffffu, c.y, 16));
+}
+// per-thread table of 8 complex constants parked in 32 TMEM columns
+__device__ __forceinline__ void tmem_park8(uint32_t taddr, const cplx (&t)[8]) { tmem_st_ta(taddr, t); }
+// 32x32b column of (slot s, im, hi): 16 s[2] + 8 im + 4 s[1] + 2 s[0] + hi
+// forward: slots s of pass-B threads -> slots p of pass-C threads
+__device__ __forceinline__ void xchg_fwd(uint32_t tq, cplx (&v)[8]) {
+  {
+    uint32_t r[32];
+#pragma unroll
+    for (int c = 0; c < 32; c++) {
+      const int sl = ((c >> 4) & 1) * 4 + ((c >> 2) & 1) * 2 + ((c >> 1) & 1);
+      r[c] = cword(v[sl], (c >> 3) & 1, c & 1);
+    }
+    tmem_st32(tq, r);
+  }
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  uint32_t a[2][16];
+  tmem_ld16x256_x4(tq, a[0]);
+  tmem_ld16x256_x4(tq + (16u << 16), a[1]);
+  tmem_wait_ld16(a[0]);
+  tmem_wait_ld16(a[1]);
+  // register 4*(2z+im) + 2h + hi of half H: z = 0 is the half this lane keeps, z = 1 the half it trades
+#pragma unroll
+  for (int H = 0; H < 2; H++)
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      v[2 * H + h] = mk(__hiloint2double((int)a[H][2 * h + 1], (int)a[H][2 * h]),
+                        __hiloint2double((int)a[H][4 + 2 * h + 1], (int)a[H][4 + 2 * h]));
+      v[4 + 2 * H + h] = shfl16(mk(__hiloint2double((int)a[H][8 + 2 * h + 1], (int)a[H][8 + 2 * h]),
+                                   __hiloint2double((int)a[H][12 + 2 * h + 1], (int)a[H][12 + 2 * h])));
+    }
+}
+// inverse: slots p of pass-C threads -> slots s of pass-B threads
+__device__ __forceinline__ void xchg_inv(uint32_t tq, cplx (&u)[8]) {
+#pragma unroll
+  for (int H = 0; H < 2; H++) {
+    uint32_t r[16];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const cplx z0 = u[2 * H + h], z1 = shfl16(u[4 + 2 * H + h]);
+      r[2 * h] = cword(z0, 0, 0); r[2 * h + 1] = cword(z0, 0, 1);
+      r[4 + 2 * h] = cword(z0, 1, 0); r[4 + 2 * h + 1] = cword(z0, 1, 1);
+      r[8 + 2 * h] = cword(z1, 0, 0); r[8 + 2 * h + 1] = cword(z1, 0, 1);
+      r[12 + 2 * h] = cword(z1, 1, 0); r[12 + 2 * h + 1] = cword(z1, 1, 1);
+    }
+    tmem_st16x256_x4(tq + ((uint32_t)(16 * H) << 16), r);
+  }
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  uint32_t r[32];
+  tmem_ld32(tq, r);
+  tmem_wait_ld32(r);
+#pragma unroll
+  for (int sl = 0; sl < 8; sl++) {
+    const int c = 16 * (sl >> 2) + 4 * ((sl >> 1) & 1) + 2 * (sl & 1);
+    u[sl] = mk(__hiloint2double((int)r[c + 1], (int)r[c]), __hiloint2double((int)r[c + 9], (int)r[c + 8]));
+  }
+}
+
+template <int L, int BGBIT, int STAGES, bool MAGIC>
+__global__ void __launch_bounds__(384, 1) blind_rotate_kernel_x(const BrArgs args) {
+  constexpr int G = 4, PW = 8, L2 = 2 * L;
+  constexpr bool EXACT = (L == 3 && BGBIT == 6);
+  constexpr int kAccBytes = 2 * kN * 4, kExchBytes = 3 * kXStride * 16, kAbarBytes = 2432;
+  constexpr int kGroupBytes = kAccBytes + kExchBytes + kAbarBytes;
+  extern __shared__ __align__(128) uint8_t smem[];
+  cplx *ring = reinterpret_cast<cplx *>(smem);
+  uint8_t *groups = smem + STAGES * kStageBytes;
+  uint64_t *full = reinterpret_cast<uint64_t *>(groups + G * kGroupBytes);
+  uint64_t *empty = full + STAGES;
+  uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(empty + STAGES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t n = args.n;
+  const uint32_t grid = gridDim.x;
+  const uint32_t rounds = (uint32_t)((args.count + grid * G - 1) / (grid * G));
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2 * G); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_base_s)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tbase = *tmem_base_s;
+  if (warp >= PW) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == PW && lane == 0) {
+      // ===== producer: stream key rows (i, r), permuted layout =====
+      const uint8_t *src0 = reinterpret_cast<const uint8_t *>(args.bsk2);
+      uint32_t stage = 0, parity = 0;
+      const uint32_t rows = n * L2;
+      for (uint32_t rd = 0; rd < rounds; rd++)
+        for (uint32_t row = 0; row < rows; row++) {
+          mbar_wait_backoff(&empty[stage], parity ^ 1);
+          mbar_arrive_expect_tx(&full[stage], kStageBytes);
+          tma_load_1d(reinterpret_cast<uint8_t *>(ring) + stage * kStageBytes, src0 + (size_t)row * kStageBytes,
+                      kStageBytes, &full[stage]);
+          if (++stage == STAGES) { stage = 0; parity ^= 1; }
+        }
+    }
+    return;
+  }
+  // ===== consumers: group g owns one ciphertext per round =====
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+  const int g = warp >> 1;
+  const int tid = threadIdx.x & 63;               // pass A / A' thread, and the key-row slot of pass C
+  const int l4 = (lane >> 4) & 1, l3 = (lane >> 3) & 1, l2 = (lane >> 2) & 1;
+  const int b_j0 = 4 * l2 + 2 * l4 + l3, b_k0 = 4 * (warp & 1) + (lane & 3);   // pass B / B' coordinates
+  const int c_k1 = 4 * l4 + (lane & 3);                                       // pass C / C' coordinate
+  const double sg_b = l2 ? -1.0 : 1.0, sg_c = l4 ? -1.0 : 1.0;
+  uint8_t *gbase = groups + g * kGroupBytes;
+  uint32_t *acc = reinterpret_cast<uint32_t *>(gbase);
+  cplx *exch = reinterpret_cast<cplx *>(gbase + kAccBytes);
+  uint16_t *abar_s = reinterpret_cast<uint16_t *>(gbase + kAccBytes + kExchBytes);
+  // TMEM columns of this warp: four parked twiddle tables of 32 columns (pass A, signed pass A',
+  // pass B by slot, pass C' by slot), then three exchange blocks
+  const uint32_t taddr = tbase + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * 256u;
+  const uint32_t t_tai = taddr + 32, t_tbf = taddr + 64, t_tbi = taddr + 96, tq = taddr + 128;
+  {
+    cplx t[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) t[k] = args.tw_a[tid * 8 + k];
+    tmem_park8(taddr, t);
+    // pass B' hands pass A' its inputs negated where j1 is odd and j0[2] is set (see dft8s)
+    const double sg_a = (((tid >> 3) & 1) && ((tid >> 2) & 1)) ? -1.0 : 1.0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) t[k] = mk(t[k].x * sg_a, t[k].y * sg_a);
+    tmem_park8(t_tai, t);
+#pragma unroll
+    for (int sl = 0; sl < 8; sl++) t[sl] = args.tw_b[b_j0 * 8 + (sl ^ (4 * l2))];   // w64^(j0 k1), k1 = s ^ 4 l2
+    tmem_park8(t_tbf, t);
+#pragma unroll
+    for (int sl = 0; sl < 8; sl++) t[sl] = args.tw_b[c_k1 * 8 + (sl ^ (4 * l4))];   // w64^(j0 k1), j0 = p ^ 4 l4
+    tmem_park8(t_tbi, t);
+  }
+  const uint32_t w = n + 1;
+  uint32_t stage = 0, parity = 0;
+  for (uint32_t rd = 0; rd < rounds; rd++) {
+    const size_t ct = ((size_t)rd * G + g) * grid + blockIdx.x;
+    const bool active = ct < args.count;
+    if (active) {
+      // ---- K0: linear pre-combination + modulus switch (trgsw.rs:202-203, 210-211)
+      uint32_t ca = 1, cb = 0, off = 0;
+      const uint32_t *A, *B;
+      if (args.op >= 0 || args.ops) {
+        int op = args.ops ? (int)args.ops[ct] : args.op;
+        ca = (uint32_t)c_gate_ca[op]; cb = (uint32_t)c_gate_cb[op]; off = c_gate_off[op];
+        A = args.in + ct * 2 * w;
+        B = A + w;
+      } else {
+        A = args.in + ct * w;
+        B = A;
+      }
+      for (uint32_t i = tid; i < n; i += 64) {
+        uint32_t v = ca * A[i] + cb * B[i];
+        abar_s[i] = (uint16_t)((uint32_t)(v + (1u << 20)) >> 21);
+      }
+      uint32_t bw = ca * A[n] + cb * B[n] + off;
+      uint32_t b_tilda = (uint32_t)(2 * kN - (((uint64_t)bw + (1u << 20)) >> 21));
+      const int tvi = args.tv_index ? args.tv_index[ct] : args.tv_default;
+      const uint32_t *tv = args.tv + (size_t)tvi * 2 * kN;
+      for (int x = tid; x < 2 * kN; x += 64)
+        acc[x] = rot_coeff(tv + (x & ~(kN - 1)), x & (kN - 1), b_tilda);
+    }
+    group_sync(g);
+    for (uint32_t i = 0; i < n; i++) {
+      if (active) {
+        cplx racc[2][8];
+        const uint32_t abar = abar_s[i];
+#pragma unroll
+        for (int o = 0; o < 2; o++)
+#pragma unroll
+          for (int k = 0; k < 8; k++) racc[o][k] = mk(0.0, 0.0);
+#pragma unroll 1
+        for (int p = 0; p < 2; p++) {
+          {
+            uint32_t t_re[8], t_im[8];
+            load_t(tid, acc + p * kN, abar, args.offset, t_re, t_im);
+            cplx ta[8];
+            tmem_ld_ta(taddr, ta);
+            fwd_pass_a<BGBIT, 0, L, MAGIC, kS, kXStride>(tid, t_re, t_im, ta, exch);
+          }
+          group_sync(g);
+          cplx tb[8];
+          tmem_ld_ta(t_tbf, tb);
+#pragma unroll
+          for (int d = 0; d < L; d++) {
+            // pass B over j1, exchange through TMEM, pass C over j0, MAC against key row (p, d)
+            const cplx *e = exch + d * kXStride + b_k0 * kS + b_j0;
+            cplx v[8];
+#pragma unroll
+            for (int j1 = 0; j1 < 8; j1++) v[j1] = e[j1 * 9];
+            dft8s<false>(v, sg_b);
+#pragma unroll
+            for (int sl = 0; sl < 8; sl++) v[sl] = cmul(v[sl], tb[sl]);
+            xchg_fwd(tq + 32 * d, v);
+            dft8<false>(v);
+            mbar_wait(&full[stage], parity);
+            const cplx *bsk_row = ring + stage * kChunkCplx;
+#pragma unroll
+            for (int k2 = 0; k2 < 8; k2++) {
+              cfma(racc[0][k2], v[k2], bsk_row[(k2 * 2 + 0) * 64 + tid]);
+              cfma(racc[1][k2], v[k2], bsk_row[(k2 * 2 + 1) * 64 + tid]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+            if (++stage == STAGES) { stage = 0; parity ^= 1; }
+          }
+          group_sync(g);   // everyone has read this polynomial's pass-A output
+        }
+        {
+          cplx tbi[8];
+          tmem_ld_ta(t_tbi, tbi);
+#pragma unroll
+          for (int o = 0; o < 2; o++) {
+            // pass C' over k2, exchange back, pass B' over k1
+            dft8s<true>(racc[o], sg_c);
+#pragma unroll
+            for (int sl = 0; sl < 8; sl++) racc[o][sl] = cmulc(racc[o][sl], tbi[sl]);
+            xchg_inv(tq + 32 * o, racc[o]);
+            dft8<true>(racc[o]);
+            cplx *e = exch + o * kXStride + b_k0 * kS + b_j0;
+#pragma unroll
+            for (int j1 = 0; j1 < 8; j1++) e[j1 * 9] = racc[o][j1];
+          }
+        }
+        group_sync(g);
+        {
+          cplx ta[8];
+          tmem_ld_ta(t_tai, ta);
+          inv_pass_a<EXACT, MAGIC, kS, kXStride>(tid, ta, exch, acc);
+        }
+        group_sync(g);
+      } else {
+        // idle group: keep the ring's phase accounting in lock step
+        for (int c = 0; c < L2; c++) {
+          mbar_wait(&full[stage], parity);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; parity ^= 1; }
+        }
+      }
+    }
+    if (active) {
+      // ---- epilogue: TRLWE, or fused sample extraction (trlwe.rs:106-136)
+      if (args.out_mode == BR_OUT_TRLWE) {
+        uint32_t *o = args.out + ct * 2 * kN;
+        for (int x = tid; x < 2 * kN; x += 64) o[x] = acc[x];
+      } else {
+        const uint32_t m = args.out_mode == BR_OUT_EXTRACT ? (uint32_t)kN : n;
+        uint32_t *o = args.out + ct * (m + 1);
+        for (uint32_t x = tid; x <= m; x += 64) {
+          uint32_t v;
+          if (x == 0) v = acc[0];
+          else if (x == m) v = acc[kN];
+          else v = ~acc[m - x];
+          o[x] = v;
+        }
+      }
+    }
+    group_sync(g);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  asm volatile("bar.sync 15, %0;" ::"n"(G * 64) : "memory");
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tbase));
+}
+template <int L, int BGBIT, bool MAGIC_REQ>
+cudaError_t launch_x(const BrArgs &args, int num_sms, cudaStream_t stream) {
+  constexpr bool MAGIC = MAGIC_REQ && L == 3 && BGBIT == 6;
+  if (!args.bsk2) return cudaErrorInvalidValue;   // engine did not build the permuted key
+  auto kern = blind_rotate_kernel_x<L, BGBIT, 4, MAGIC>;
+  const int smem = 4 * kStageBytes + 4 * (2 * kN * 4 + 3 * kXStride * 16 + 2432) + 2 * 4 * 8 + 16;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  int grid = (int)(args.count < (size_t)num_sms ? args.count : (size_t)num_sms);
+  if (grid < 1) grid = 1;
+  kern<<<grid, 384, smem, stream>>>(args);
+  return cudaGetLastError();
 }
 
 // ---- V4: six groups per SM ------------------------------------------------------------
@@ -886,17 +1545,19 @@ cudaError_t launch_latency(const BrArgs &args, int num_sms, cudaStream_t stream)
   return cudaGetLastError();
 }
 
-template <int L, int BGBIT, int G, int STAGES, int NBUF, bool TMEM_TW, int RC, int RP, bool PARK = false>
+template <int L, int BGBIT, int G, int STAGES, int NBUF, bool TMEM_TW, int RC, int RP, bool PARK = false,
+          int CPW = 1, bool MAGIC_REQ = false, bool SPLIT = true>
 cudaError_t launch_v(const BrArgs &args, int num_sms, cudaStream_t stream) {
-  auto kern = blind_rotate_kernel<L, BGBIT, G, STAGES, NBUF, TMEM_TW, RC, RP, PARK>;
-  const int smem = STAGES * kStageBytes + G * Cfg<L, NBUF>::kGroupBytes + 2 * STAGES * 8 + 16;
+  constexpr bool MAGIC = MAGIC_REQ && L == 3 && BGBIT == 6;
+  auto kern = blind_rotate_kernel<L, BGBIT, G, STAGES, NBUF, TMEM_TW, RC, RP, PARK, CPW, MAGIC, SPLIT>;
+  const int smem = STAGES * kStageBytes + G * Cfg<L, NBUF>::kGroupBytes + 128 + 2 * STAGES * 8 + 16;
   {  // per device and cheap: set on every launch (engines may live on several GPUs)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
   }
   int grid = (int)(args.count < (size_t)num_sms ? args.count : (size_t)num_sms);
   if (grid < 1) grid = 1;
-  kern<<<grid, ((2 * G + 3) / 4) * 128 + 128, smem, stream>>>(args);
+  kern<<<grid, SPLIT ? ((2 * G + 3) / 4) * 128 + 128 : 2 * G * 32 + 32, smem, stream>>>(args);
   return cudaGetLastError();
 }
 
@@ -905,7 +1566,7 @@ int br_variant() {
   if (v < 0) {
     const char *e = getenv("TFHE_BR_VARIANT");
     v = e ? atoi(e) : BR_DEFAULT_VARIANT;
-    if (v < 1 || v > 6) v = BR_DEFAULT_VARIANT;
+    if (v < 1 || v > 19) v = BR_DEFAULT_VARIANT;
   }
   return v;
 }
@@ -924,6 +1585,24 @@ template <int L, int BGBIT>
 cudaError_t launch_t(const BrArgs &args, int num_sms, cudaStream_t stream) {
   if (L > 1 && args.count <= (size_t)br_latency_threshold(num_sms))
     return launch_latency<L, BGBIT>(args, num_sms, stream);
+  // 7/8: variant 3 with 2/4 ciphertexts interleaved per warp (broadcast key reads);
+  // 9/10/11: CPW = 1/2/4 with the 2^52-bias conversions
+  if (br_variant() == 7) return launch_v<L, BGBIT, 4, 4, 3, true, 232, 40, false, 2>(args, num_sms, stream);
+  if (br_variant() == 8) return launch_v<L, BGBIT, 4, 4, 3, true, 232, 40, false, 4>(args, num_sms, stream);
+  if (br_variant() == 9) return launch_v<L, BGBIT, 4, 4, 3, true, 232, 40, false, 1, true>(args, num_sms, stream);
+  if (br_variant() == 10) return launch_v<L, BGBIT, 4, 4, 3, true, 232, 40, false, 2, true>(args, num_sms, stream);
+  if (br_variant() == 11) return launch_v<L, BGBIT, 4, 4, 3, true, 232, 40, false, 4, true>(args, num_sms, stream);
+  // 12/13/14: key rows staged in TMEM (tcgen05.cp broadcast), 2-slot shared ring + 6/4/7-row TMEM ring
+  if (br_variant() == 12) return launch_tmem<L, BGBIT, 2, 6, true>(args, num_sms, stream);
+  if (br_variant() == 13) return launch_tmem<L, BGBIT, 2, 4, true>(args, num_sms, stream);
+  if (br_variant() == 14) return launch_tmem<L, BGBIT, 3, 7, false>(args, num_sms, stream);
+  // 17: five groups at the launch-time 184 registers (no warpgroup split), 2-slot ring
+  if (br_variant() == 17) return launch_v<L, BGBIT, 5, 2, 3, true, 0, 0, false, 1, true, false>(args, num_sms, stream);
+  if (br_variant() == 18) return launch_v<L, BGBIT, 5, 2, 3, true, 0, 0, true, 1, true, false>(args, num_sms, stream);
+  // 19: pass B<->C exchange through tensor memory + one shuffle stage (permuted key layout)
+  if (br_variant() == 19) return launch_x<L, BGBIT, true>(args, num_sms, stream);
+  if (br_variant() == 15) return launch_tmem<L, BGBIT, 2, 6, true, 1>(args, num_sms, stream);
+  if (br_variant() == 16) return launch_tmem<L, BGBIT, 2, 6, true, 2>(args, num_sms, stream);
   if (br_variant() == 4) return launch_v4<L, BGBIT>(args, num_sms, stream);
   if (br_variant() == 6)  // five groups per SM at 160 registers (3 exchange buffers, 2-stage ring)
     return launch_v<L, BGBIT, 5, 2, 3, true, 160, 24, true>(args, num_sms, stream);
@@ -937,6 +1616,8 @@ cudaError_t launch_t(const BrArgs &args, int num_sms, cudaStream_t stream) {
 }
 
 }  // namespace
+
+bool br_uses_permuted_key() { return br_variant() == 19; }
 
 bool br_supported(uint32_t l, uint32_t bgbit) {
   return (l == 3 && bgbit == 6) || (l == 2 && bgbit == 10) || (l == 1 && bgbit == 18) ||

@@ -84,6 +84,25 @@ template <bool INV> BR_HD void dft8(cplx (&v)[8]) {
   v[3] = cfma_s(c2, s, q3); v[7] = cfma_s(c2, -s, q3);
 }
 
+// Same butterfly with a per-thread sign sg = +-1 in the last stage: sg = -1 delivers the outputs
+// with slots k and k^4 swapped (equivalently: the transform of the input with its odd elements
+// negated).  Same instruction count -- the four plain complex add/sub pairs become FMAs.
+template <bool INV> BR_HD void dft8s(cplx (&v)[8], double sg) {
+  const double s = 0.70710678118654752440 * sg;
+  cplx a0 = cadd(v[0], v[4]), a4 = csub(v[0], v[4]);
+  cplx a1 = cadd(v[1], v[5]), p5 = mul_w1u<INV>(csub(v[1], v[5]));
+  cplx a2 = cadd(v[2], v[6]), a6 = mul_i<INV>(csub(v[2], v[6]));
+  cplx a3 = cadd(v[3], v[7]), p7 = mul_w3u<INV>(csub(v[3], v[7]));
+  cplx b0 = cadd(a0, a2), b2 = csub(a0, a2);
+  cplx b1 = cadd(a1, a3), b3 = mul_i<INV>(csub(a1, a3));
+  v[0] = cfma_s(b0, sg, b1); v[4] = cfma_s(b0, -sg, b1);
+  v[2] = cfma_s(b2, sg, b3); v[6] = cfma_s(b2, -sg, b3);
+  cplx c0 = cadd(a4, a6), c2 = csub(a4, a6);
+  cplx q1 = cadd(p5, p7), q3 = mul_i<INV>(csub(p5, p7));
+  v[1] = cfma_s(c0, s, q1); v[5] = cfma_s(c0, -s, q1);
+  v[3] = cfma_s(c2, s, q3); v[7] = cfma_s(c2, -s, q3);
+}
+
 // (re + i im) * omega^(64 M) and its conjugate form, with the trivial cases spelled out
 // (M = 0: nothing; M = 4: one real factor) so no multiply-by-one/zero is issued
 template <int M> BR_HD cplx pre_w();
@@ -133,6 +152,24 @@ template <bool EXACT> BR_HD uint32_t round_torus(double y) {
 #endif
 }
 
+// Exact-regime conversions without the conversion pipe: a small unsigned u becomes the double
+// 2^52 + u by bit pattern, one exact DADD removes the bias; y + 1.5*2^52 leaves round-to-nearest-
+// even(y) mod 2^32 in the low mantissa word (|y| < 2^51; the exact regime is bounded by 2^48.6).
+BR_HD double biased_to_double(uint32_t u, double bias) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(0x43300000, (int)u) - bias;
+#else
+  return (4503599627370496.0 + (double)u) - bias;
+#endif
+}
+BR_HD uint32_t round_torus_magic(double y) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__double2loint(y + 6755399441055744.0);
+#else
+  return round_torus<true>(y);
+#endif
+}
+
 // ---- rotate-and-subtract (trgsw.rs:212-215 + :183-186 fused) -----------------
 // (X^abar * acc - acc)[j], with the reference's Torus::MAX - x wrap (trgsw.rs:318,322)
 BR_HD uint32_t rot_diff(const uint32_t *accp, int j, uint32_t abar) {
@@ -177,17 +214,21 @@ BR_HD void load_t(int tid, const uint32_t *accp, uint32_t abar, uint32_t offset,
 // Pass A for digits [D0, D0+ND) of one polynomial (decomposition trgsw.rs:161-167 fused
 // with the twist, klemsa.rs:96-103): thread tid owns complex points 64m+tid; digit d goes
 // to exchange buffer d-D0.
-template <int BGBIT, int D0, int ND>
+template <int BGBIT, int D0, int ND, bool MAGIC = false, int S = 72, int STRIDE = kExchStride>
 BR_HD void fwd_pass_a(int tid, const uint32_t (&t_re)[8], const uint32_t (&t_im)[8],
                       const cplx (&ta)[8], cplx *exch) {
   constexpr uint32_t MASK = (1u << BGBIT) - 1u;
   constexpr int HALFBG = 1 << (BGBIT - 1);
+  constexpr double BIAS = 4503599627370496.0 + (double)HALFBG;
 #pragma unroll
   for (int d = D0; d < D0 + ND; d++) {
     const int sh = 32 - (d + 1) * BGBIT;
     cplx v[8];
 #define BR_LOAD(M)                                                              \
-  {                                                                             \
+  if (MAGIC) {                                                                  \
+    v[M] = twist_in<M>(biased_to_double((t_re[M] >> sh) & MASK, BIAS),          \
+                       biased_to_double((t_im[M] >> sh) & MASK, BIAS));         \
+  } else {                                                                      \
     int dre = (int)((t_re[M] >> sh) & MASK) - HALFBG;                            \
     int dim = (int)((t_im[M] >> sh) & MASK) - HALFBG;                            \
     v[M] = twist_in<M>((double)dre, (double)dim);                               \
@@ -195,9 +236,9 @@ BR_HD void fwd_pass_a(int tid, const uint32_t (&t_re)[8], const uint32_t (&t_im)
     BR_LOAD(0) BR_LOAD(1) BR_LOAD(2) BR_LOAD(3) BR_LOAD(4) BR_LOAD(5) BR_LOAD(6) BR_LOAD(7)
 #undef BR_LOAD
     dft8<false>(v);
-    cplx *e = exch + (d - D0) * kExchStride + tid + (tid >> 3);
+    cplx *e = exch + (d - D0) * STRIDE + tid + (tid >> 3);
 #pragma unroll
-    for (int k0 = 0; k0 < 8; k0++) e[k0 * 72] = cmul(v[k0], ta[k0]);
+    for (int k0 = 0; k0 < 8; k0++) e[k0 * S] = cmul(v[k0], ta[k0]);
   }
 }
 
@@ -306,21 +347,26 @@ BR_HD void inv_pass_b(int tid, cplx *exch) {
 
 // Pass A' + untwist + torus rounding (klemsa.rs:136-147) + accumulator update
 // (trgsw.rs:190-193).  acc points at this ciphertext's u32[2][1024].
-template <bool EXACT>
+template <bool EXACT, bool MAGIC = false, int S = 72, int STRIDE = kExchStride>
 BR_HD void inv_pass_a(int tid, const cplx (&ta)[8], const cplx *exch, uint32_t *acc) {
 #pragma unroll
   for (int o = 0; o < 2; o++) {
-    const cplx *e = exch + o * kExchStride + tid + (tid >> 3);
+    const cplx *e = exch + o * STRIDE + tid + (tid >> 3);
     cplx v[8];
 #pragma unroll
-    for (int k0 = 0; k0 < 8; k0++) v[k0] = cmulc(e[k0 * 72], ta[k0]);
+    for (int k0 = 0; k0 < 8; k0++) v[k0] = cmulc(e[k0 * S], ta[k0]);
     dft8<true>(v);
     uint32_t *ap = acc + o * kN;
 #define BR_STORE(M)                                                       \
   {                                                                       \
     cplx y = twist_out<M>(v[M]);                                          \
-    ap[64 * M + tid] += round_torus<EXACT>(y.x);                          \
-    ap[64 * M + tid + kHalf] += round_torus<EXACT>(y.y);                  \
+    if (MAGIC) {                                                          \
+      ap[64 * M + tid] += round_torus_magic(y.x);                         \
+      ap[64 * M + tid + kHalf] += round_torus_magic(y.y);                 \
+    } else {                                                              \
+      ap[64 * M + tid] += round_torus<EXACT>(y.x);                        \
+      ap[64 * M + tid + kHalf] += round_torus<EXACT>(y.y);                \
+    }                                                                     \
   }
     BR_STORE(0) BR_STORE(1) BR_STORE(2) BR_STORE(3) BR_STORE(4) BR_STORE(5) BR_STORE(6) BR_STORE(7)
 #undef BR_STORE

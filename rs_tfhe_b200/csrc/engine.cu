@@ -61,6 +61,7 @@ struct tfhe_engine {
   std::mutex mu;
   // cloud key: one contiguous device blob = BSK | KSK | test-vector slots
   uint8_t *blob = nullptr;
+  cplx *bsk2 = nullptr;   // BSK rows in the TMEM-exchange kernel's thread order (derived, not in the blob)
   size_t blob_bytes = 0, off_ksk = 0, off_kmma = 0, off_tv = 0;
   bool has_kmma = false;  // basebit == 2: tensor-pipe key switch available
   bool key_loaded = false;
@@ -112,6 +113,17 @@ void blob_layout(tfhe_engine *e) {
   e->blob_bytes = e->off_tv + (size_t)kMaxLut * 2 * TFHE_N * 4;
 }
 
+// Derived key material: rebuilt whenever the blob's BSK changes (upload, generation, commit, import).
+int finalize_key(tfhe_engine *e) {
+  if (!br_uses_permuted_key()) return TFHE_OK;
+  const size_t rows = (size_t)e->p.n * 2 * e->p.l;
+  if (!e->bsk2) CU(cudaMalloc(reinterpret_cast<void **>(&e->bsk2), rows * br::kChunkCplx * sizeof(cplx)));
+  CU(bsk_permute_launch(e->bsk(), e->bsk2, rows, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  e->launches++;
+  return TFHE_OK;
+}
+
 int ensure_blob(tfhe_engine *e) {
   if (e->blob) return TFHE_OK;
   blob_layout(e);
@@ -149,6 +161,7 @@ int run_device(tfhe_engine *e, tfhe_engine::Slot &sl, int op, const uint8_t *d_o
   if (lut_id >= e->n_lut) return fail(TFHE_ERR_INVALID, "unknown lut id %d", lut_id);
   BrArgs a{};
   a.bsk = e->bsk();
+  a.bsk2 = e->bsk2;
   a.tw_a = e->tw_a; a.tw_b = e->tw_b;
   a.tv = e->tv(); a.tv_index = d_lut_ids; a.tv_default = lut_id < 0 ? 0 : lut_id;
   a.in = d_in; a.ops = d_ops; a.op = op;
@@ -333,6 +346,7 @@ void tfhe_engine_destroy(tfhe_engine *e) {
   cudaSetDevice(e->dev);
   cudaDeviceSynchronize();
   if (e->blob) cudaFree(e->blob);
+  if (e->bsk2) cudaFree(e->bsk2);
   if (e->tw_a) cudaFree(e->tw_a);
   if (e->tw_b) cudaFree(e->tw_b);
   e->s_misc.release();
@@ -420,6 +434,7 @@ int tfhe_engine_load_cloud_key(tfhe_engine *e, uint32_t decomposition_offset,
   e->s_misc.release();
   e->decomp_offset = decomposition_offset;
   e->n_lut = 1;
+  { int rc_ = finalize_key(e); if (rc_ != TFHE_OK) return rc_; }
   e->key_loaded = true;
   return TFHE_OK;
 }
@@ -466,6 +481,7 @@ int tfhe_engine_generate_cloud_key(tfhe_engine *e, const uint32_t *s0, const uin
   for (uint32_t i = 0; i < p.l; i++) offset += (1u << (p.bgbit - 1)) << (32 - (i + 1) * p.bgbit);
   e->decomp_offset = offset;
   e->n_lut = 1;
+  { int rc_ = finalize_key(e); if (rc_ != TFHE_OK) return rc_; }
   e->key_loaded = true;
   return TFHE_OK;
 }
@@ -491,6 +507,7 @@ int tfhe_engine_commit_cloud_key(tfhe_engine *e, uint32_t decomposition_offset) 
   std::lock_guard<std::mutex> lock(e->mu);
   e->decomp_offset = decomposition_offset;
   e->n_lut = 1;
+  { int rc_ = finalize_key(e); if (rc_ != TFHE_OK) return rc_; }
   e->key_loaded = true;
   return TFHE_OK;
 }
@@ -551,6 +568,7 @@ int tfhe_engine_import_cloud_key(tfhe_engine *e, const void *host_buf, size_t by
   CU(cudaStreamSynchronize(e->stream));
   e->decomp_offset = hd.decomposition_offset;
   e->n_lut = (int)hd.n_lut;
+  { int rc_ = finalize_key(e); if (rc_ != TFHE_OK) return rc_; }
   e->key_loaded = true;
   return TFHE_OK;
 }

@@ -12,6 +12,7 @@ enum { BR_OUT_TRLWE = 0, BR_OUT_EXTRACT = 1, BR_OUT_EXTRACT2 = 2 };
 // K0+K3 (blind_rotate.cu)
 struct BrArgs {
   const cplx *bsk;          // device order: cplx[n][2l][8][2][64] (br_core.cuh)
+  const cplx *bsk2;         // same rows, thread slots permuted for the TMEM-exchange kernel (or NULL)
   const cplx *tw_a;         // [64][8]
   const cplx *tw_b;         // [8][8]
   const uint32_t *tv;       // test vectors u32[slot][2][N]; slot 0 = cloud-key test vector
@@ -27,6 +28,7 @@ struct BrArgs {
   size_t count;
 };
 bool br_supported(uint32_t l, uint32_t bgbit);
+bool br_uses_permuted_key();  // the selected throughput kernel reads BrArgs::bsk2
 cudaError_t br_launch(uint32_t l, uint32_t bgbit, const BrArgs &args, int num_sms,
                       cudaStream_t stream);
 
@@ -61,6 +63,7 @@ cudaError_t ksk_mma_relayout_launch(const uint32_t *src_ref, uint32_t *dst, uint
 // layout / small kernels (aux.cu)
 cudaError_t bsk_relayout_launch(const double *src_ref, cplx *dst, uint32_t n, uint32_t l2,
                                 cudaStream_t stream);
+cudaError_t bsk_permute_launch(const cplx *src, cplx *dst, size_t rows, cudaStream_t stream);
 cudaError_t ksk_relayout_launch(const uint32_t *src_ref, uint32_t *dst, uint32_t rows, uint32_t n,
                                 uint32_t stride, cudaStream_t stream);
 cudaError_t lut_generate_launch(const uint32_t *d_f_table, uint32_t modulus, double scale,
