@@ -26,7 +26,7 @@ using namespace br;
 #define BR_PRODUCER_SLEEP_NS 256
 #endif
 #ifndef BR_DEFAULT_VARIANT
-#define BR_DEFAULT_VARIANT 3
+#define BR_DEFAULT_VARIANT 8
 #endif
 
 namespace {
@@ -84,9 +84,6 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
 }
 __device__ __forceinline__ void group_sync(int g) {
   asm volatile("bar.sync %0, 64;" ::"r"(g + 1) : "memory");
-}
-template <int THREADS> __device__ __forceinline__ void group_sync_n(int g) {
-  asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(THREADS) : "memory");
 }
 
 // gates.rs:54-150: out = ca*a + cb*b, b-word += off
@@ -191,24 +188,14 @@ template <int L, int NBUF> struct Cfg {
 //   V1: G=4 groups, 3 exchange buffers, twiddles in registers   (consumers 232 regs)
 //   V2: G=6 groups, 2 exchange buffers (digits in sub-rounds of <=2), pass-A twiddles in
 //       TMEM, pass-B twiddles rebuilt from three base values     (consumers 160 regs)
-//   CPW ("ciphertexts per warp", 1/2/4): a warp carries 32/CPW lanes of each of CPW ciphertexts
-//       that sit at the same ring position, so the lanes of different ciphertexts read the SAME
-//       key words in the MAC and shared memory serves them as one broadcast wavefront.
 //   MAGIC: int<->double conversions of the exact regime as 2^52-biased bit patterns + one DADD
 //       (FP64 pipe) instead of I2F/F2I (quarter-rate conversion pipe).
 template <int L, int BGBIT, int G, int STAGES, int NBUF, bool TMEM_TW, int REGS_CONS, int REGS_PROD,
-          bool PARK = false, int CPW = 1, bool MAGIC = false, bool SPLIT = true>
-__global__ void __launch_bounds__(SPLIT ? ((2 * G + 3) / 4) * 128 + 128 : 2 * G * 32 + 32, 1)
-    blind_rotate_kernel(const BrArgs args) {
-  static_assert(CPW == 1 || (G % CPW == 0 && (CPW == 2 || CPW == 4)), "CPW must divide G");
+          bool PARK = false, bool MAGIC = false>
+__global__ void __launch_bounds__(((2 * G + 3) / 4) * 128 + 128, 1) blind_rotate_kernel(const BrArgs args) {
   static_assert(!MAGIC || (L == 3 && BGBIT == 6), "MAGIC conversions need the exact regime");
-  constexpr int LPC = 32 / CPW;        // lanes per ciphertext in a warp
-  constexpr int GT = 64 * CPW;         // threads that share group barriers
-  constexpr int kPad = CPW > 1 ? 128 / CPW : 0;  // bank rotation between the ciphertexts of a warp
   using C = Cfg<L, NBUF>;
-  // SPLIT: producer in its own warpgroup, registers rebalanced with setmaxnreg; !SPLIT: one extra
-  // warp after the consumers, every warp keeps the launch-time register count (65536/blockDim)
-  constexpr int PW = SPLIT ? ((2 * G + 3) / 4) * 4 : 2 * G;
+  constexpr int PW = ((2 * G + 3) / 4) * 4;  // first producer warp: its own warpgroup
   constexpr int L2 = 2 * L;
   constexpr bool EXACT = (L == 3 && BGBIT == 6);
   static_assert(NBUF >= 2 && (L <= NBUF || (L == 3 && NBUF == 2)), "unsupported buffer plan");
@@ -217,7 +204,7 @@ __global__ void __launch_bounds__(SPLIT ? ((2 * G + 3) / 4) * 128 + 128 : 2 * G 
   extern __shared__ __align__(128) uint8_t smem[];
   cplx *ring = reinterpret_cast<cplx *>(smem);
   uint8_t *groups = smem + STAGES * kStageBytes;
-  uint64_t *full = reinterpret_cast<uint64_t *>(groups + G * C::kGroupBytes + 128);
+  uint64_t *full = reinterpret_cast<uint64_t *>(groups + G * C::kGroupBytes);
   uint64_t *empty = full + STAGES;
   uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(empty + STAGES);
 
@@ -247,7 +234,7 @@ __global__ void __launch_bounds__(SPLIT ? ((2 * G + 3) / 4) * 128 + 128 : 2 * G 
   // consumer warps, so the launch is compiled at 65536/blockDim registers/thread and
   // rebalanced here (SASS: USETMAXREG).
   if (warp >= PW) {
-    if constexpr (SPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PROD));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PROD));
     // ===== producer: stream BSK rows (i, r) for every round =====
     if (warp == PW && lane == 0) {
       const uint8_t *src0 = reinterpret_cast<const uint8_t *>(args.bsk);
@@ -267,13 +254,11 @@ __global__ void __launch_bounds__(SPLIT ? ((2 * G + 3) / 4) * 128 + 128 : 2 * G 
   }
 
   // ===== consumers: group g owns one ciphertext per round =====
-  if constexpr (SPLIT) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_CONS));
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_CONS));
   if (warp >= 2 * G) return;  // padding warps of a partially filled consumer warpgroup (odd G)
-  const int gg = warp / (2 * CPW);                       // barrier group (CPW ciphertexts)
-  const int q = lane / LPC;                              // which of the warp's ciphertexts
-  const int g = gg * CPW + q;                            // ciphertext slot in the CTA
-  const int tid = (warp % (2 * CPW)) * LPC + (lane % LPC);
-  uint8_t *gbase = groups + g * C::kGroupBytes + q * kPad;
+  const int g = warp >> 1;
+  const int tid = threadIdx.x & 63;
+  uint8_t *gbase = groups + g * C::kGroupBytes;
   uint32_t *acc = reinterpret_cast<uint32_t *>(gbase);
   cplx *exch = reinterpret_cast<cplx *>(gbase + C::kAccBytes);
   uint16_t *abar_s = reinterpret_cast<uint16_t *>(gbase + C::kAccBytes + C::kExchBytes);
@@ -344,13 +329,10 @@ __global__ void __launch_bounds__(SPLIT ? ((2 * G + 3) / 4) * 128 + 128 : 2 * G 
       for (int x = tid; x < 2 * kN; x += 64)
         acc[x] = rot_coeff(tv + (x & ~(kN - 1)), x & (kN - 1), b_tilda);
     }
-    group_sync_n<GT>(gg);
+    group_sync(g);
 
-    // with CPW > 1 the lanes of an idle tail ciphertext ride along on whatever its buffers hold
-    // (every u32 is a valid torus word); only their loads and stores are masked
-    const bool warp_active = CPW == 1 ? active : (__ballot_sync(0xffffffffu, active) != 0u);
     for (uint32_t i = 0; i < n; i++) {
-      if (warp_active) {
+      if (active) {
         cplx racc[2][8];
         const uint32_t abar = abar_s[i];
 #pragma unroll
@@ -365,12 +347,12 @@ __global__ void __launch_bounds__(SPLIT ? ((2 * G + 3) / 4) * 128 + 128 : 2 * G 
             BR_GET_TA(ta)
             fwd_pass_a<BGBIT, 0, ND0, MAGIC>(tid, t_re, t_im, ta, exch);
           }
-          group_sync_n<GT>(gg);
+          group_sync(g);
           {
             BR_GET_TB(tb)
             fwd_pass_b<ND0>(tid, tb, exch);
           }
-          group_sync_n<GT>(gg);
+          group_sync(g);
           if (PARK && p == 1) {   // accumulators were parked in TMEM during poly b's passes A/B
             unpark8(taddr + 32, racc[0]);
             unpark8(taddr + 64, racc[1]);
@@ -381,34 +363,34 @@ __global__ void __launch_bounds__(SPLIT ? ((2 * G + 3) / 4) * 128 + 128 : 2 * G 
             park8(taddr + 64, racc[1]);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           }
-          group_sync_n<GT>(gg);
+          group_sync(g);
           if constexpr (ND1 > 0) {
             {
               BR_GET_TA(ta)
               fwd_pass_a<BGBIT, ND0, ND1, MAGIC>(tid, t_re, t_im, ta, exch);
             }
-            group_sync_n<GT>(gg);
+            group_sync(g);
             {
               BR_GET_TB(tb)
               fwd_pass_b<ND1>(tid, tb, exch);
             }
-            group_sync_n<GT>(gg);
+            group_sync(g);
             BR_MAC_DIGITS(ND1)
-            group_sync_n<GT>(gg);
+            group_sync(g);
           }
         }
         {
           BR_GET_TB(tb)
           inv_pass_c(tid, tb, racc, exch);
         }
-        group_sync_n<GT>(gg);
+        group_sync(g);
         inv_pass_b(tid, exch);
-        group_sync_n<GT>(gg);
+        group_sync(g);
         {
           BR_GET_TA(ta)
           inv_pass_a<EXACT, MAGIC>(tid, ta, exch, acc);
         }
-        group_sync_n<GT>(gg);
+        group_sync(g);
       } else {
         // idle group: keep the ring's phase accounting in lock step
         for (int c = 0; c < L2; c++) {
@@ -437,7 +419,7 @@ __global__ void __launch_bounds__(SPLIT ? ((2 * G + 3) / 4) * 128 + 128 : 2 * G 
         }
       }
     }
-    group_sync_n<GT>(gg);
+    group_sync(g);
   }
 #undef BR_GET_TA
 #undef BR_GET_TB
@@ -449,33 +431,6 @@ __global__ void __launch_bounds__(SPLIT ? ((2 * G + 3) / 4) * 128 + 128 : 2 * G 
   }
 }
 
-// ---- TMEM-staged key rows ----------------------------------------------------------------------
-// In the kernel above every group re-reads each staged key row from shared memory (4 x 16 KB per
-// row: a quarter of all shared-memory wavefronts, and the MAC phase is the most shared-memory-
-// bound one).  Here a row goes global -> shared (TMA, as before) -> TENSOR MEMORY with
-// tcgen05.cp 64x128b.warpx2::02_13: one copy instruction moves the 64 x 16 B slice of one
-// (k2, o) pair and multicasts rows 0-31 to lane quadrants 0 and 2, rows 32-63 to quadrants 1 and
-// 3 -- exactly the TMEM lanes of the even / odd warps of every group -- so each consumer thread
-// finds its 16 key words of the row in 64 consecutive columns of its own TMEM lane and reads
-// them with tcgen05.ld (12-cycle latency, own data path).  Shared memory is read once per row
-// instead of four times; the shared ring shrinks to SSTAGES slots and the TMEM ring holds TSTAGES
-// rows, so groups can drift a whole step apart.
-//   warp PW   lane 0: TMA producer   (waits empty[s]  <- tcgen05.commit of the copies that read slot s)
-//   warp PW+1 lane 0: copy issuer    (waits full[s], tempty[t]; 16 x tcgen05.cp; commits -> empty[s], tfull[t])
-//   consumers       : wait tfull[t]; tcgen05.ld; MAC; arrive tempty[t]
-__device__ __forceinline__ uint64_t smem_desc_noswizzle(uint32_t saddr) {
-  // K-major, SWIZZLE_NONE: 8-row x 16 B core matrices, 128 B apart in both directions; version 1
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) |
-         ((uint64_t)1 << 46);
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
 // completion of every outstanding tcgen05.ld of this thread; the loaded registers are threaded
 // through as in/out operands so no use can be scheduled above the wait
 __device__ __forceinline__ void tmem_wait_ld16(uint32_t (&r)[16]) {
@@ -484,269 +439,6 @@ __device__ __forceinline__ void tmem_wait_ld16(uint32_t (&r)[16]) {
                  "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
                :
                : "memory");
-}
-__device__ __forceinline__ cplx cplx_from_words(const uint32_t *w) {
-  return mk(__hiloint2double((int)w[1], (int)w[0]), __hiloint2double((int)w[3], (int)w[2]));
-}
-// pass C + MAC with the key row in TMEM: columns [(k2*2+o)*4, +4) of this thread's lane
-__device__ __forceinline__ void fwd_pass_c_mac_tmem(int tid, const cplx *exch_d, uint32_t trow, cplx (&acc)[2][8]) {
-  const cplx *e = exch_d + tid * 9;
-  cplx v[8];
-#pragma unroll
-  for (int j0 = 0; j0 < 8; j0++) v[j0] = e[j0];
-  uint32_t b0[16], b1[16];
-  tmem_ld16(trow, b0);
-  dft8<false>(v);
-#pragma unroll
-  for (int c = 0; c < 4; c++) {
-    if (c & 1) tmem_wait_ld16(b1); else tmem_wait_ld16(b0);
-    if (c < 3) { if (c & 1) tmem_ld16(trow + 16 * (c + 1), b0); else tmem_ld16(trow + 16 * (c + 1), b1); }
-    const uint32_t *b = (c & 1) ? b1 : b0;
-#pragma unroll
-    for (int kk = 0; kk < 2; kk++) {
-      cfma(acc[0][2 * c + kk], v[2 * c + kk], cplx_from_words(b + kk * 8));
-      cfma(acc[1][2 * c + kk], v[2 * c + kk], cplx_from_words(b + kk * 8 + 4));
-    }
-  }
-}
-
-template <int L, int BGBIT, int SSTAGES, int TSTAGES, bool MAGIC, int EXP = 0>
-__global__ void __launch_bounds__(384, 1) blind_rotate_kernel_t(const BrArgs args) {
-  constexpr int G = 4, NBUF = 3, PW = 8, L2 = 2 * L;
-  using C = Cfg<L, NBUF>;
-  constexpr bool EXACT = (L == 3 && BGBIT == 6);
-  static_assert(L <= NBUF, "one sub-round per polynomial");
-  static_assert(64 + TSTAGES * 64 <= 512, "TMEM columns");
-  constexpr uint32_t kKeyCol0 = 64;   // TMEM columns [0,64): pass-A twiddles; then TSTAGES rows of 64 columns
-  extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t *ring = smem;
-  uint8_t *groups = smem + SSTAGES * kStageBytes;
-  uint64_t *full = reinterpret_cast<uint64_t *>(groups + G * C::kGroupBytes);
-  uint64_t *empty = full + SSTAGES;
-  uint64_t *tfull = empty + SSTAGES;
-  uint64_t *tempty = tfull + TSTAGES;
-  uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(tempty + TSTAGES);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t n = args.n;
-  const uint32_t grid = gridDim.x;
-  const uint32_t per_round = grid * G;
-  const uint32_t rounds = (uint32_t)((args.count + per_round - 1) / per_round);
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < SSTAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int t = 0; t < TSTAGES; t++) { mbar_init(&tfull[t], 1); mbar_init(&tempty[t], 2 * G); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
-        smem_u32(tmem_base_s)));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;");
-  const uint32_t tbase = *tmem_base_s;
-
-  if (warp >= PW) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    const uint32_t rows = n * L2;
-    if (warp == PW && lane == 0) {
-      // ===== TMA producer: key rows global -> shared ring =====
-      const uint8_t *src0 = reinterpret_cast<const uint8_t *>(args.bsk);
-      uint32_t stage = 0, parity = 0;
-      for (uint32_t rd = 0; rd < rounds; rd++)
-        for (uint32_t row = 0; row < rows; row++) {
-          mbar_wait_backoff(&empty[stage], parity ^ 1);
-          mbar_arrive_expect_tx(&full[stage], kStageBytes);
-          tma_load_1d(ring + stage * kStageBytes, src0 + (size_t)row * kStageBytes, kStageBytes, &full[stage]);
-          if (++stage == SSTAGES) { stage = 0; parity ^= 1; }
-        }
-    } else if (warp == PW + 1 && lane == 0) {
-      // ===== copy issuer: shared ring -> TMEM ring (SASS: UTCCP) =====
-      uint32_t stage = 0, parity = 0, ts = 0, tparity = 0;
-      for (uint32_t rd = 0; rd < rounds; rd++)
-        for (uint32_t row = 0; row < rows; row++) {
-          mbar_wait_backoff(&tempty[ts], tparity ^ 1);
-          mbar_wait_backoff(&full[stage], parity);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t src = smem_u32(ring + stage * kStageBytes);
-          const uint32_t dst = tbase + kKeyCol0 + ts * 64;
-#pragma unroll
-          for (int sl = 0; sl < (EXP == 2 ? 0 : 16); sl++)   // EXP 2 (timing experiment, wrong results): no copies
-            asm volatile("tcgen05.cp.cta_group::1.64x128b.warpx2::02_13 [%0], %1;" ::"r"(dst + 4 * sl),
-                         "l"(smem_desc_noswizzle(src + sl * 1024))
-                         : "memory");
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                           smem_u32(&empty[stage]))
-                       : "memory");
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                           smem_u32(&tfull[ts]))
-                       : "memory");
-          if (++stage == SSTAGES) { stage = 0; parity ^= 1; }
-          if (++ts == TSTAGES) { ts = 0; tparity ^= 1; }
-        }
-    }
-    return;
-  }
-
-  // ===== consumers: group g owns one ciphertext per round =====
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-  const int g = warp >> 1;
-  const int tid = threadIdx.x & 63;
-  uint8_t *gbase = groups + g * C::kGroupBytes;
-  uint32_t *acc = reinterpret_cast<uint32_t *>(gbase);
-  cplx *exch = reinterpret_cast<cplx *>(gbase + C::kAccBytes);
-  uint16_t *abar_s = reinterpret_cast<uint16_t *>(gbase + C::kAccBytes + C::kExchBytes);
-
-  const uint32_t tlane = tbase + (((uint32_t)(warp & 3) * 32u) << 16);
-  const uint32_t taddr = tlane + (uint32_t)(warp >> 2) * 32u;
-  cplx tb1, tb2, tb4;
-  {
-    const cplx *twb = args.tw_b + (tid & 7) * 8;
-    tb1 = twb[1]; tb2 = twb[2]; tb4 = twb[4];
-    cplx ta[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) ta[k] = args.tw_a[tid * 8 + k];
-    tmem_st_ta(taddr, ta);
-  }
-
-  const uint32_t w = n + 1;
-  uint32_t ts = 0, tparity = 0;
-
-  for (uint32_t rd = 0; rd < rounds; rd++) {
-    const size_t ct = ((size_t)rd * G + g) * grid + blockIdx.x;
-    const bool active = ct < args.count;
-
-    if (active) {
-      // ---- K0: linear pre-combination + modulus switch (trgsw.rs:202-203, 210-211)
-      uint32_t ca = 1, cb = 0, off = 0;
-      const uint32_t *A, *B;
-      if (args.op >= 0 || args.ops) {
-        int op = args.ops ? (int)args.ops[ct] : args.op;
-        ca = (uint32_t)c_gate_ca[op]; cb = (uint32_t)c_gate_cb[op]; off = c_gate_off[op];
-        A = args.in + ct * 2 * w;
-        B = A + w;
-      } else {
-        A = args.in + ct * w;
-        B = A;
-      }
-      for (uint32_t i = tid; i < n; i += 64) {
-        uint32_t v = ca * A[i] + cb * B[i];
-        abar_s[i] = (uint16_t)((uint32_t)(v + (1u << 20)) >> 21);
-      }
-      uint32_t bw = ca * A[n] + cb * B[n] + off;
-      uint32_t b_tilda = (uint32_t)(2 * kN - (((uint64_t)bw + (1u << 20)) >> 21));
-      const int tvi = args.tv_index ? args.tv_index[ct] : args.tv_default;
-      const uint32_t *tv = args.tv + (size_t)tvi * 2 * kN;
-      for (int x = tid; x < 2 * kN; x += 64)
-        acc[x] = rot_coeff(tv + (x & ~(kN - 1)), x & (kN - 1), b_tilda);
-    }
-    group_sync(g);
-
-    for (uint32_t i = 0; i < n; i++) {
-      if (active) {
-        cplx racc[2][8];
-        const uint32_t abar = abar_s[i];
-#pragma unroll
-        for (int o = 0; o < 2; o++)
-#pragma unroll
-          for (int k = 0; k < 8; k++) racc[o][k] = mk(0.0, 0.0);
-#pragma unroll 1
-        for (int p = 0; p < 2; p++) {
-          uint32_t t_re[8], t_im[8];
-          load_t(tid, acc + p * kN, abar, args.offset, t_re, t_im);
-          {
-            cplx ta[8];
-            tmem_ld_ta(taddr, ta);
-            fwd_pass_a<BGBIT, 0, L, MAGIC>(tid, t_re, t_im, ta, exch);
-          }
-          group_sync(g);
-          {
-            cplx tb[8];
-            expand_tb(tb1, tb2, tb4, tb);
-            fwd_pass_b<L>(tid, tb, exch);
-          }
-          group_sync(g);
-#pragma unroll
-          for (int d = 0; d < L; d++) {
-            mbar_wait(&tfull[ts], tparity);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (EXP == 1)   // timing experiment (wrong results): copies run, consumers read the shared ring instead
-              fwd_pass_c_mac(tid, exch + d * kExchStride, reinterpret_cast<const cplx *>(ring) + (ts % SSTAGES) * kChunkCplx, racc);
-            else
-              fwd_pass_c_mac_tmem(tid, exch + d * kExchStride, tlane + kKeyCol0 + ts * 64, racc);
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[ts]);
-            if (++ts == TSTAGES) { ts = 0; tparity ^= 1; }
-          }
-          group_sync(g);
-        }
-        {
-          cplx tb[8];
-          expand_tb(tb1, tb2, tb4, tb);
-          inv_pass_c(tid, tb, racc, exch);
-        }
-        group_sync(g);
-        inv_pass_b(tid, exch);
-        group_sync(g);
-        {
-          cplx ta[8];
-          tmem_ld_ta(taddr, ta);
-          inv_pass_a<EXACT, MAGIC>(tid, ta, exch, acc);
-        }
-        group_sync(g);
-      } else {
-        // idle group: keep the TMEM ring's phase accounting in lock step
-        for (int c = 0; c < L2; c++) {
-          mbar_wait(&tfull[ts], tparity);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[ts]);
-          if (++ts == TSTAGES) { ts = 0; tparity ^= 1; }
-        }
-      }
-    }
-
-    if (active) {
-      // ---- epilogue: TRLWE, or fused sample extraction (trlwe.rs:106-136)
-      if (args.out_mode == BR_OUT_TRLWE) {
-        uint32_t *o = args.out + ct * 2 * kN;
-        for (int x = tid; x < 2 * kN; x += 64) o[x] = acc[x];
-      } else {
-        const uint32_t m = args.out_mode == BR_OUT_EXTRACT ? (uint32_t)kN : n;
-        uint32_t *o = args.out + ct * (m + 1);
-        for (uint32_t x = tid; x <= m; x += 64) {
-          uint32_t v;
-          if (x == 0) v = acc[0];
-          else if (x == m) v = acc[kN];
-          else v = ~acc[m - x];
-          o[x] = v;
-        }
-      }
-    }
-    group_sync(g);
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  asm volatile("bar.sync 15, %0;" ::"n"(G * 64) : "memory");  // all consumers done with TMEM
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  if (warp == 0)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tbase));
-}
-
-template <int L, int BGBIT, int SSTAGES, int TSTAGES, bool MAGIC_REQ, int EXP = 0>
-cudaError_t launch_tmem(const BrArgs &args, int num_sms, cudaStream_t stream) {
-  constexpr bool MAGIC = MAGIC_REQ && L == 3 && BGBIT == 6;
-  auto kern = blind_rotate_kernel_t<L, BGBIT, SSTAGES, TSTAGES, MAGIC, EXP>;
-  const int smem = SSTAGES * kStageBytes + 4 * Cfg<L, 3>::kGroupBytes + (2 * SSTAGES + 2 * TSTAGES) * 8 + 16;
-  {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-  }
-  int grid = (int)(args.count < (size_t)num_sms ? args.count : (size_t)num_sms);
-  if (grid < 1) grid = 1;
-  kern<<<grid, 384, smem, stream>>>(args);
-  return cudaGetLastError();
 }
 
 // ---- intra-warp FFT exchange through tensor memory ---------------------------------------------
@@ -809,6 +501,7 @@ __device__ __forceinline__ cplx shfl16(const cplx &c) {
 __device__ __forceinline__ void tmem_park8(uint32_t taddr, const cplx (&t)[8]) { tmem_st_ta(taddr, t); }
 // 32x32b column of (slot s, im, hi): 16 s[2] + 8 im + 4 s[1] + 2 s[0] + hi
 // forward: slots s of pass-B threads -> slots p of pass-C threads
+// (one 32-column store: four 8-column stores measured 3 % slower, tools/exp_variants.py)
 __device__ __forceinline__ void xchg_fwd(uint32_t tq, cplx (&v)[8]) {
   {
     uint32_t r[32];
@@ -865,6 +558,8 @@ __device__ __forceinline__ void xchg_inv(uint32_t tq, cplx (&u)[8]) {
 template <int L, int BGBIT, int STAGES, bool MAGIC>
 __global__ void __launch_bounds__(384, 1) blind_rotate_kernel_x(const BrArgs args) {
   constexpr int G = 4, PW = 8, L2 = 2 * L;
+  constexpr int kTmemCols = 256;   // per warp: 4 parked tables + 3 exchange blocks of 32 columns
+  constexpr int kXBlk = 32;        // distance between the digits' exchange blocks
   constexpr bool EXACT = (L == 3 && BGBIT == 6);
   constexpr int kAccBytes = 2 * kN * 4, kExchBytes = 3 * kXStride * 16, kAbarBytes = 2432;
   constexpr int kGroupBytes = kAccBytes + kExchBytes + kAbarBytes;
@@ -922,7 +617,7 @@ __global__ void __launch_bounds__(384, 1) blind_rotate_kernel_x(const BrArgs arg
   uint16_t *abar_s = reinterpret_cast<uint16_t *>(gbase + kAccBytes + kExchBytes);
   // TMEM columns of this warp: four parked twiddle tables of 32 columns (pass A, signed pass A',
   // pass B by slot, pass C' by slot), then three exchange blocks
-  const uint32_t taddr = tbase + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * 256u;
+  const uint32_t taddr = tbase + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * kTmemCols;
   const uint32_t t_tai = taddr + 32, t_tbf = taddr + 64, t_tbi = taddr + 96, tq = taddr + 128;
   {
     cplx t[8];
@@ -1001,7 +696,7 @@ __global__ void __launch_bounds__(384, 1) blind_rotate_kernel_x(const BrArgs arg
             dft8s<false>(v, sg_b);
 #pragma unroll
             for (int sl = 0; sl < 8; sl++) v[sl] = cmul(v[sl], tb[sl]);
-            xchg_fwd(tq + 32 * d, v);
+            xchg_fwd(tq + kXBlk * d, v);
             dft8<false>(v);
             mbar_wait(&full[stage], parity);
             const cplx *bsk_row = ring + stage * kChunkCplx;
@@ -1025,7 +720,7 @@ __global__ void __launch_bounds__(384, 1) blind_rotate_kernel_x(const BrArgs arg
             dft8s<true>(racc[o], sg_c);
 #pragma unroll
             for (int sl = 0; sl < 8; sl++) racc[o][sl] = cmulc(racc[o][sl], tbi[sl]);
-            xchg_inv(tq + 32 * o, racc[o]);
+            xchg_inv(tq + kXBlk * o, racc[o]);
             dft8<true>(racc[o]);
             cplx *e = exch + o * kXStride + b_k0 * kS + b_j0;
 #pragma unroll
@@ -1076,9 +771,10 @@ __global__ void __launch_bounds__(384, 1) blind_rotate_kernel_x(const BrArgs arg
 template <int L, int BGBIT, bool MAGIC_REQ>
 cudaError_t launch_x(const BrArgs &args, int num_sms, cudaStream_t stream) {
   constexpr bool MAGIC = MAGIC_REQ && L == 3 && BGBIT == 6;
+  constexpr int STAGES = 4, G = 4;
   if (!args.bsk2) return cudaErrorInvalidValue;   // engine did not build the permuted key
-  auto kern = blind_rotate_kernel_x<L, BGBIT, 4, MAGIC>;
-  const int smem = 4 * kStageBytes + 4 * (2 * kN * 4 + 3 * kXStride * 16 + 2432) + 2 * 4 * 8 + 16;
+  auto kern = blind_rotate_kernel_x<L, BGBIT, STAGES, MAGIC>;
+  const int smem = STAGES * kStageBytes + G * (2 * kN * 4 + 3 * kXStride * 16 + 2432) + 2 * STAGES * 8 + 16;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   int grid = (int)(args.count < (size_t)num_sms ? args.count : (size_t)num_sms);
@@ -1546,18 +1242,18 @@ cudaError_t launch_latency(const BrArgs &args, int num_sms, cudaStream_t stream)
 }
 
 template <int L, int BGBIT, int G, int STAGES, int NBUF, bool TMEM_TW, int RC, int RP, bool PARK = false,
-          int CPW = 1, bool MAGIC_REQ = false, bool SPLIT = true>
+          bool MAGIC_REQ = false>
 cudaError_t launch_v(const BrArgs &args, int num_sms, cudaStream_t stream) {
   constexpr bool MAGIC = MAGIC_REQ && L == 3 && BGBIT == 6;
-  auto kern = blind_rotate_kernel<L, BGBIT, G, STAGES, NBUF, TMEM_TW, RC, RP, PARK, CPW, MAGIC, SPLIT>;
-  const int smem = STAGES * kStageBytes + G * Cfg<L, NBUF>::kGroupBytes + 128 + 2 * STAGES * 8 + 16;
+  auto kern = blind_rotate_kernel<L, BGBIT, G, STAGES, NBUF, TMEM_TW, RC, RP, PARK, MAGIC>;
+  const int smem = STAGES * kStageBytes + G * Cfg<L, NBUF>::kGroupBytes + 2 * STAGES * 8 + 16;
   {  // per device and cheap: set on every launch (engines may live on several GPUs)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
   }
   int grid = (int)(args.count < (size_t)num_sms ? args.count : (size_t)num_sms);
   if (grid < 1) grid = 1;
-  kern<<<grid, SPLIT ? ((2 * G + 3) / 4) * 128 + 128 : 2 * G * 32 + 32, smem, stream>>>(args);
+  kern<<<grid, ((2 * G + 3) / 4) * 128 + 128, smem, stream>>>(args);
   return cudaGetLastError();
 }
 
@@ -1566,7 +1262,7 @@ int br_variant() {
   if (v < 0) {
     const char *e = getenv("TFHE_BR_VARIANT");
     v = e ? atoi(e) : BR_DEFAULT_VARIANT;
-    if (v < 1 || v > 19) v = BR_DEFAULT_VARIANT;
+    if (v < 1 || v > 8) v = BR_DEFAULT_VARIANT;
   }
   return v;
 }
@@ -1585,24 +1281,10 @@ template <int L, int BGBIT>
 cudaError_t launch_t(const BrArgs &args, int num_sms, cudaStream_t stream) {
   if (L > 1 && args.count <= (size_t)br_latency_threshold(num_sms))
     return launch_latency<L, BGBIT>(args, num_sms, stream);
-  // 7/8: variant 3 with 2/4 ciphertexts interleaved per warp (broadcast key reads);
-  // 9/10/11: CPW = 1/2/4 with the 2^52-bias conversions
-  if (br_variant() == 7) return launch_v<L, BGBIT, 4, 4, 3, true, 232, 40, false, 2>(args, num_sms, stream);
-  if (br_variant() == 8) return launch_v<L, BGBIT, 4, 4, 3, true, 232, 40, false, 4>(args, num_sms, stream);
-  if (br_variant() == 9) return launch_v<L, BGBIT, 4, 4, 3, true, 232, 40, false, 1, true>(args, num_sms, stream);
-  if (br_variant() == 10) return launch_v<L, BGBIT, 4, 4, 3, true, 232, 40, false, 2, true>(args, num_sms, stream);
-  if (br_variant() == 11) return launch_v<L, BGBIT, 4, 4, 3, true, 232, 40, false, 4, true>(args, num_sms, stream);
-  // 12/13/14: key rows staged in TMEM (tcgen05.cp broadcast), 2-slot shared ring + 6/4/7-row TMEM ring
-  if (br_variant() == 12) return launch_tmem<L, BGBIT, 2, 6, true>(args, num_sms, stream);
-  if (br_variant() == 13) return launch_tmem<L, BGBIT, 2, 4, true>(args, num_sms, stream);
-  if (br_variant() == 14) return launch_tmem<L, BGBIT, 3, 7, false>(args, num_sms, stream);
-  // 17: five groups at the launch-time 184 registers (no warpgroup split), 2-slot ring
-  if (br_variant() == 17) return launch_v<L, BGBIT, 5, 2, 3, true, 0, 0, false, 1, true, false>(args, num_sms, stream);
-  if (br_variant() == 18) return launch_v<L, BGBIT, 5, 2, 3, true, 0, 0, true, 1, true, false>(args, num_sms, stream);
-  // 19: pass B<->C exchange through tensor memory + one shuffle stage (permuted key layout)
-  if (br_variant() == 19) return launch_x<L, BGBIT, true>(args, num_sms, stream);
-  if (br_variant() == 15) return launch_tmem<L, BGBIT, 2, 6, true, 1>(args, num_sms, stream);
-  if (br_variant() == 16) return launch_tmem<L, BGBIT, 2, 6, true, 2>(args, num_sms, stream);
+  // 8 (default): pass B<->C exchange through tensor memory + one shuffle stage (permuted key layout)
+  if (br_variant() == 8) return launch_x<L, BGBIT, true>(args, num_sms, stream);
+  // 7: variant 3 with the 2^52-bias conversions
+  if (br_variant() == 7) return launch_v<L, BGBIT, 4, 4, 3, true, 232, 40, false, true>(args, num_sms, stream);
   if (br_variant() == 4) return launch_v4<L, BGBIT>(args, num_sms, stream);
   if (br_variant() == 6)  // five groups per SM at 160 registers (3 exchange buffers, 2-stage ring)
     return launch_v<L, BGBIT, 5, 2, 3, true, 160, 24, true>(args, num_sms, stream);
@@ -1617,7 +1299,7 @@ cudaError_t launch_t(const BrArgs &args, int num_sms, cudaStream_t stream) {
 
 }  // namespace
 
-bool br_uses_permuted_key() { return br_variant() == 19; }
+bool br_uses_permuted_key() { return br_variant() == 8; }
 
 bool br_supported(uint32_t l, uint32_t bgbit) {
   return (l == 3 && bgbit == 6) || (l == 2 && bgbit == 10) || (l == 1 && bgbit == 18) ||
