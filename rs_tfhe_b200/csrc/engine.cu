@@ -211,13 +211,21 @@ int run_host(tfhe_engine *e, int op, const uint8_t *ops, int lut_id, const uint3
   CU(cudaSetDevice(e->dev));
   if (!e->key_loaded) return fail(TFHE_ERR_NO_KEY, "cloud key not loaded");
   float ms0 = 0.f, ms1 = 0.f;
-  const size_t chunk = (size_t)e->num_sms * 4 * 28;  // 28 rounds of the persistent grid
+  // Chunks are whole rounds of the persistent grid (4 ciphertexts per SM): 28 rounds in steady
+  // state, but a short first chunk (its upload is the only one no kernel hides) and a short last
+  // one (likewise its download).
+  const size_t round = (size_t)e->num_sms * 4;
+  const size_t chunk = round * 28, edge = round * 4;
   // order after whatever the caller queued on the engine stream
   CU(cudaEventRecord(e->ev[3], e->stream));
   CU(cudaStreamWaitEvent(e->copy_in, e->ev[3], 0));
   int k = 0;
-  for (size_t base = 0; base < count; base += chunk, k++) {
-    const size_t c = count - base < chunk ? count - base : chunk;
+  for (size_t base = 0, c = 0; base < count; base += c, k++) {
+    const size_t left = count - base;
+    if (base == 0 && left > 2 * edge) c = edge;
+    else if (left > chunk + edge) c = chunk;
+    else if (left > 2 * edge) c = left - edge;
+    else c = left;
     tfhe_engine::Slot &sl = e->slot[k & 1];
     int rc = retire_slot(sl, ms0, ms1);
     if (rc != TFHE_OK) return rc;
