@@ -105,3 +105,78 @@ extern "C" int emu_blind_rotate(uint32_t n, uint32_t l, uint32_t bgbit, uint32_t
   else return -1;
   return 0;
 }
+
+// ---- model of the tcgen05 key switch (keyswitch_umma.cu) -----------------------------------
+// Same index arithmetic as the device code (ku_layout.h): emu_ku_build_key is the relayout
+// kernel; emu_ku_key_switch walks CTA tiles, pipeline stages, K steps and accumulator halves as the
+// kernel does, builds the one-hot words with the builder warps' expression, and reads the B
+// operand through the canonical K-major / no-swizzle addressing the MMA applies
+// (B[row][k] at (row/8)*256 + (k/16)*128 + (row%8)*16 + k%16).  Checked against the oracle's
+// identity_key_switching in tests/test_ks_umma_layout.py.
+#include "ku_layout.h"
+
+extern "C" size_t emu_ku_key_words(uint32_t n, uint32_t t) { return ku::key_words(n, t); }
+
+extern "C" void emu_ku_build_key(const uint32_t *ksk_ref /*[1024*t*4][n+1]*/, uint32_t n, uint32_t t,
+                                 uint32_t *dst) {
+  const size_t total = ku::key_words(n, t);
+  for (size_t idx = 0; idx < total; idx++) {
+    const ku::Src s = ku::decode(idx, t);
+    uint32_t v = 0;
+    if (s.x <= n)
+      for (uint32_t k = 1; k < 4; k++) {
+        const uint32_t wv = ksk_ref[((size_t)s.q * 4 + k) * (n + 1) + s.x];
+        v |= ((wv >> (8 * s.plane)) & 0xFFu) << (8 * k);
+      }
+    dst[idx] = v;
+  }
+}
+
+extern "C" int emu_ku_key_switch(const uint32_t *key_words, const uint32_t *ext /*[count][1025]*/,
+                                 size_t count, uint32_t n, uint32_t t, uint32_t *out /*[count][n+1]*/) {
+  if (t < 7 || t > 9) return -1;
+  const uint8_t *key = reinterpret_cast<const uint8_t *>(key_words);
+  const uint32_t nst = ku::n_stages(t), prec = 1u << (32 - (1 + 2 * t));
+  const size_t mtiles = (count + ku::kM - 1) / ku::kM;
+  std::vector<int32_t> D(ku::kCols);
+  for (uint32_t nt = 0; nt < ku::n_tiles(n); nt++)
+    for (size_t mt = 0; mt < mtiles; mt++)
+      for (int row = 0; row < ku::kM; row++) {
+        const size_t ct = mt * ku::kM + row;
+        if (ct >= count) break;
+        std::fill(D.begin(), D.end(), 0);
+        uint32_t st = 0;
+        for (uint32_t blk = 0; blk < ku::kRing / 16; blk++) {     // builder: 16 coefficients
+          uint32_t ab[16];
+          for (int c = 0; c < 16; c++) ab[c] = ext[ct * (ku::kRing + 1) + 16 * blk + c] + prec;
+          for (uint32_t s = 0; s < t; s++, st++) {                // one pipeline stage
+            uint32_t r[16];
+            for (int c = 0; c < 16; c++) {
+              const uint32_t qb = 16 * s + c, il = qb / t, j = qb % t;
+              r[c] = 1u << ((ab[il] >> (27 - 2 * j)) & 0x18u);
+            }
+            const uint8_t *stage = key + ((size_t)nt * nst + st) * ku::kStageBytes;
+            for (int ks = 0; ks < 2; ks++)
+              for (int h = 0; h < 2; h++) {
+                const uint8_t *tile = stage + (ks * 2 + h) * ku::kTileBytes;
+                for (int k = 0; k < ku::kStepK; k++) {
+                  const uint32_t a = (r[ks * 8 + k / 4] >> (8 * (k % 4))) & 0xFFu;  // A[row][k]
+                  if (!a) continue;
+                  for (int nr = 0; nr < ku::kHalf; nr++)
+                    D[h * ku::kHalf + nr] +=
+                        (int32_t)(a * tile[(nr / 8) * 256 + (k / 16) * 128 + (nr % 8) * 16 + k % 16]);
+                }
+              }
+          }
+        }
+        for (int xl = 0; xl < ku::kWords; xl++) {                 // epilogue
+          const uint32_t x = nt * ku::kWords + xl;
+          if (x > n) break;
+          const uint32_t sum = (uint32_t)D[4 * xl] + ((uint32_t)D[4 * xl + 1] << 8) +
+                               ((uint32_t)D[4 * xl + 2] << 16) + ((uint32_t)D[4 * xl + 3] << 24);
+          const uint32_t init = (x == n) ? ext[ct * (ku::kRing + 1) + ku::kRing] : 0u;
+          out[ct * (n + 1) + x] = init - sum;
+        }
+      }
+  return 0;
+}

@@ -14,6 +14,10 @@
 
 #include "kernels.h"
 
+#ifndef TFHE_KS_DEFAULT
+#define TFHE_KS_DEFAULT 0   // 0 = tcgen05 (umma), 1 = mma.sync, 2 = row walk
+#endif
+
 namespace {
 
 thread_local char g_err[512] = "";
@@ -62,6 +66,7 @@ struct tfhe_engine {
   // cloud key: one contiguous device blob = BSK | KSK | test-vector slots
   uint8_t *blob = nullptr;
   cplx *bsk2 = nullptr;   // BSK rows in the TMEM-exchange kernel's thread order (derived, not in the blob)
+  uint8_t *kumma = nullptr;  // KSK as tcgen05 operand tiles (derived from the blob's KSK rows; gate sets)
   size_t blob_bytes = 0, off_ksk = 0, off_kmma = 0, off_tv = 0;
   bool has_kmma = false;  // basebit == 2: tensor-pipe key switch available
   bool key_loaded = false;
@@ -113,14 +118,32 @@ void blob_layout(tfhe_engine *e) {
   e->blob_bytes = e->off_tv + (size_t)kMaxLut * 2 * TFHE_N * 4;
 }
 
+// K4 kernel selection: TFHE_KS_VARIANT = umma (default: tcgen05.mma, TMEM accumulators) | mma
+// (mma.sync, register accumulators) | rows (row-walk kernels; always used when basebit != 2).
+enum { KS_UMMA = 0, KS_MMA = 1, KS_ROWS = 2 };
+int ks_variant() {
+  static const int v = [] {
+    const char *s = getenv("TFHE_KS_VARIANT");
+    if (!s || !s[0]) return (int)TFHE_KS_DEFAULT;
+    return s[0] == 'r' ? (int)KS_ROWS : s[0] == 'm' ? (int)KS_MMA : (int)KS_UMMA;
+  }();
+  return v;
+}
+
 // Derived key material: rebuilt whenever the blob's BSK changes (upload, generation, commit, import).
 int finalize_key(tfhe_engine *e) {
-  if (!br_uses_permuted_key()) return TFHE_OK;
-  const size_t rows = (size_t)e->p.n * 2 * e->p.l;
-  if (!e->bsk2) CU(cudaMalloc(reinterpret_cast<void **>(&e->bsk2), rows * br::kChunkCplx * sizeof(cplx)));
-  CU(bsk_permute_launch(e->bsk(), e->bsk2, rows, e->stream));
+  if (br_uses_permuted_key()) {
+    const size_t rows = (size_t)e->p.n * 2 * e->p.l;
+    if (!e->bsk2) CU(cudaMalloc(reinterpret_cast<void **>(&e->bsk2), rows * br::kChunkCplx * sizeof(cplx)));
+    CU(bsk_permute_launch(e->bsk(), e->bsk2, rows, e->stream));
+    e->launches++;
+  }
+  if (ks_variant() == KS_UMMA && ks_umma_supported(e->p.basebit, e->p.iks_t)) {
+    if (!e->kumma) CU(cudaMalloc(reinterpret_cast<void **>(&e->kumma), ks_umma_key_bytes(e->p.n, e->p.iks_t)));
+    CU(ksk_umma_relayout_launch(e->ksk(), e->ksk_stride, e->kumma, e->p.n, e->p.iks_t, e->stream));
+    e->launches++;
+  }
   CU(cudaStreamSynchronize(e->stream));
-  e->launches++;
   return TFHE_OK;
 }
 
@@ -131,11 +154,15 @@ int ensure_blob(tfhe_engine *e) {
   return TFHE_OK;
 }
 
-// K4 dispatch: tensor-pipe GEMM for the gate sets, row-walk kernels otherwise
-// (TFHE_KS_VARIANT=rows forces the row-walk kernels for A/B measurements).
+// K4 dispatch: tensor-core GEMM for the gate sets, row-walk kernels otherwise
 int key_switch(tfhe_engine *e, const uint32_t *d_ext, uint32_t *d_out, size_t count) {
-  static const bool rows_only = [] { const char *v = getenv("TFHE_KS_VARIANT"); return v && v[0] == 'r'; }();
-  if (e->has_kmma && !rows_only) {
+  const int variant = ks_variant();
+  if (variant == KS_UMMA && e->kumma) {
+    KsUmmaArgs k{};
+    k.key = e->kumma; k.ext = d_ext; k.out = d_out;
+    k.n = e->p.n; k.iks_t = e->p.iks_t; k.count = count;
+    CU(ks_umma_launch(k, e->stream));
+  } else if (e->has_kmma && variant != KS_ROWS) {
     KsMmaArgs k{};
     k.w = e->kmma(); k.ext = d_ext; k.out = d_out;
     k.n = e->p.n; k.iks_t = e->p.iks_t; k.nxg = ks_mma_nxg(e->p.n); k.count = count;
@@ -355,6 +382,7 @@ void tfhe_engine_destroy(tfhe_engine *e) {
   cudaDeviceSynchronize();
   if (e->blob) cudaFree(e->blob);
   if (e->bsk2) cudaFree(e->bsk2);
+  if (e->kumma) cudaFree(e->kumma);
   if (e->tw_a) cudaFree(e->tw_a);
   if (e->tw_b) cudaFree(e->tw_b);
   e->s_misc.release();

@@ -1,6 +1,6 @@
 """Every selectable kernel variant stays bit-exact: the experimental blind-rotation variants
 (TFHE_BR_VARIANT=1..8 with the small-batch latency kernel disabled; 8 -- the FFT exchange through
-tensor memory -- is the default throughput variant, 3 the previous one, and TFHE_BR_LATENCY_MAX selects up to which batch size the latency kernel runs) and the row-walk key switch (TFHE_KS_VARIANT=rows,
+tensor memory -- is the default throughput variant, 3 the previous one, and TFHE_BR_LATENCY_MAX selects up to which batch size the latency kernel runs) and the key-switch kernels (TFHE_KS_VARIANT=umma -- tcgen05, the default --, mma, rows,
 TFHE_KS_GENERIC=1) run tools/sanitize.py -- mixed gates, LUT bootstrap, blind rotate +
 extract/key switch, each compared word for word with the oracle -- in their own process
 (the selectors are read once per process)."""
@@ -20,6 +20,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     {"TFHE_BR_VARIANT": "5", "TFHE_BR_LATENCY_MAX": "0"}, {"TFHE_BR_VARIANT": "6", "TFHE_BR_LATENCY_MAX": "0"},
     {"TFHE_BR_VARIANT": "7", "TFHE_BR_LATENCY_MAX": "0"}, {"TFHE_BR_VARIANT": "8", "TFHE_BR_LATENCY_MAX": "0"},
     {"TFHE_BR_LATENCY_MAX": "1000"},
+    {"TFHE_BR_VARIANT": "9", "TFHE_BR_LATENCY_MAX": "0"},
+    {"TFHE_KS_VARIANT": "umma"}, {"TFHE_KS_VARIANT": "mma"},
     {"TFHE_KS_VARIANT": "rows"}, {"TFHE_KS_VARIANT": "rows", "TFHE_KS_GENERIC": "1"},
 ], ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
 def test_variant_bit_exact(env):
