@@ -555,7 +555,7 @@ __device__ __forceinline__ void xchg_inv(uint32_t tq, cplx (&u)[8]) {
   }
 }
 
-template <int L, int BGBIT, int STAGES, bool MAGIC, int RC = 232, int RP = 40>
+template <int L, int BGBIT, int STAGES, bool MAGIC>
 __global__ void __launch_bounds__(384, 1) blind_rotate_kernel_x(const BrArgs args) {
   constexpr int G = 4, PW = 8, L2 = 2 * L;
   constexpr int kTmemCols = 256;   // per warp: 4 parked tables + 3 exchange blocks of 32 columns
@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(384, 1) blind_rotate_kernel_x(const BrArgs arg
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tbase = *tmem_base_s;
   if (warp >= PW) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RP));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == PW && lane == 0) {
       // ===== producer: stream key rows (i, r), permuted layout =====
       const uint8_t *src0 = reinterpret_cast<const uint8_t *>(args.bsk2);
@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(384, 1) blind_rotate_kernel_x(const BrArgs arg
     return;
   }
   // ===== consumers: group g owns one ciphertext per round =====
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(RC));
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
   const int g = warp >> 1;
   const int tid = threadIdx.x & 63;               // pass A / A' thread, and the key-row slot of pass C
   const int l4 = (lane >> 4) & 1, l3 = (lane >> 3) & 1, l2 = (lane >> 2) & 1;
@@ -768,12 +768,12 @@ __global__ void __launch_bounds__(384, 1) blind_rotate_kernel_x(const BrArgs arg
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tbase));
 }
-template <int L, int BGBIT, bool MAGIC_REQ, int RC = 232, int RP = 40>
+template <int L, int BGBIT, bool MAGIC_REQ>
 cudaError_t launch_x(const BrArgs &args, int num_sms, cudaStream_t stream) {
   constexpr bool MAGIC = MAGIC_REQ && L == 3 && BGBIT == 6;
   constexpr int STAGES = 4, G = 4;
   if (!args.bsk2) return cudaErrorInvalidValue;   // engine did not build the permuted key
-  auto kern = blind_rotate_kernel_x<L, BGBIT, STAGES, MAGIC, RC, RP>;
+  auto kern = blind_rotate_kernel_x<L, BGBIT, STAGES, MAGIC>;
   const int smem = STAGES * kStageBytes + G * (2 * kN * 4 + 3 * kXStride * 16 + 2432) + 2 * STAGES * 8 + 16;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
@@ -1262,7 +1262,7 @@ int br_variant() {
   if (v < 0) {
     const char *e = getenv("TFHE_BR_VARIANT");
     v = e ? atoi(e) : BR_DEFAULT_VARIANT;
-    if (v < 1 || v > 9) v = BR_DEFAULT_VARIANT;
+    if (v < 1 || v > 8) v = BR_DEFAULT_VARIANT;
   }
   return v;
 }
@@ -1283,8 +1283,6 @@ cudaError_t launch_t(const BrArgs &args, int num_sms, cudaStream_t stream) {
     return launch_latency<L, BGBIT>(args, num_sms, stream);
   // 8 (default): pass B<->C exchange through tensor memory + one shuffle stage (permuted key layout)
   if (br_variant() == 8) return launch_x<L, BGBIT, true>(args, num_sms, stream);
-  // 9: variant 8 with the register split 240 (consumers) / 24 (producer warpgroup)
-  if (br_variant() == 9) return launch_x<L, BGBIT, true, 240, 24>(args, num_sms, stream);
   // 7: variant 3 with the 2^52-bias conversions
   if (br_variant() == 7) return launch_v<L, BGBIT, 4, 4, 3, true, 232, 40, false, true>(args, num_sms, stream);
   if (br_variant() == 4) return launch_v4<L, BGBIT>(args, num_sms, stream);
@@ -1301,7 +1299,7 @@ cudaError_t launch_t(const BrArgs &args, int num_sms, cudaStream_t stream) {
 
 }  // namespace
 
-bool br_uses_permuted_key() { return br_variant() >= 8; }
+bool br_uses_permuted_key() { return br_variant() == 8; }
 
 bool br_supported(uint32_t l, uint32_t bgbit) {
   return (l == 3 && bgbit == 6) || (l == 2 && bgbit == 10) || (l == 1 && bgbit == 18) ||

@@ -20,7 +20,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     {"TFHE_BR_VARIANT": "5", "TFHE_BR_LATENCY_MAX": "0"}, {"TFHE_BR_VARIANT": "6", "TFHE_BR_LATENCY_MAX": "0"},
     {"TFHE_BR_VARIANT": "7", "TFHE_BR_LATENCY_MAX": "0"}, {"TFHE_BR_VARIANT": "8", "TFHE_BR_LATENCY_MAX": "0"},
     {"TFHE_BR_LATENCY_MAX": "1000"},
-    {"TFHE_BR_VARIANT": "9", "TFHE_BR_LATENCY_MAX": "0"},
     {"TFHE_KS_VARIANT": "umma"}, {"TFHE_KS_VARIANT": "mma"},
     {"TFHE_KS_VARIANT": "rows"}, {"TFHE_KS_VARIANT": "rows", "TFHE_KS_GENERIC": "1"},
 ], ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
