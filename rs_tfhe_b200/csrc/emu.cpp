@@ -115,28 +115,33 @@ extern "C" int emu_blind_rotate(uint32_t n, uint32_t l, uint32_t bgbit, uint32_t
 // identity_key_switching in tests/test_ks_umma_layout.py.
 #include "ku_layout.h"
 
-extern "C" size_t emu_ku_key_words(uint32_t n, uint32_t t) { return ku::key_words(n, t); }
+extern "C" size_t emu_ku_key_words(uint32_t n, uint32_t t, uint32_t basebit) {
+  return ku::key_words(n, t, basebit);
+}
 
-extern "C" void emu_ku_build_key(const uint32_t *ksk_ref /*[1024*t*4][n+1]*/, uint32_t n, uint32_t t,
-                                 uint32_t *dst) {
-  const size_t total = ku::key_words(n, t);
+extern "C" void emu_ku_build_key(const uint32_t *ksk_ref /*[1024*t*2^basebit][n+1]*/, uint32_t n,
+                                 uint32_t t, uint32_t basebit, uint32_t *dst) {
+  const size_t total = ku::key_words(n, t, basebit);
   for (size_t idx = 0; idx < total; idx++) {
-    const ku::Src s = ku::decode(idx, t);
+    const ku::Src s = ku::decode(idx, t, basebit);
     uint32_t v = 0;
     if (s.x <= n)
-      for (uint32_t k = 1; k < 4; k++) {
-        const uint32_t wv = ksk_ref[((size_t)s.q * 4 + k) * (n + 1) + s.x];
-        v |= ((wv >> (8 * s.plane)) & 0xFFu) << (8 * k);
+      for (uint32_t b = 0; b < 4; b++) {
+        if (s.k0 + b == 0) continue;
+        const uint32_t wv = ksk_ref[((size_t)s.row0 + b) * (n + 1) + s.x];
+        v |= ((wv >> (8 * s.plane)) & 0xFFu) << (8 * b);
       }
     dst[idx] = v;
   }
 }
 
 extern "C" int emu_ku_key_switch(const uint32_t *key_words, const uint32_t *ext /*[count][1025]*/,
-                                 size_t count, uint32_t n, uint32_t t, uint32_t *out /*[count][n+1]*/) {
-  if (t < 7 || t > 9) return -1;
+                                 size_t count, uint32_t n, uint32_t t, uint32_t bb,
+                                 uint32_t *out /*[count][n+1]*/) {
+  if (bb < 2 || bb > 6) return -1;
   const uint8_t *key = reinterpret_cast<const uint8_t *>(key_words);
-  const uint32_t nst = ku::n_stages(t), prec = 1u << (32 - (1 + 2 * t));
+  const uint32_t nst = ku::n_stages(t, bb), prec = 1u << (32 - (1 + bb * t));
+  const uint32_t P = 1u << bb, pps = ku::kStageK / P, spb = 16 * t / pps;
   const size_t mtiles = (count + ku::kM - 1) / ku::kM;
   std::vector<int32_t> D(ku::kCols);
   for (uint32_t nt = 0; nt < ku::n_tiles(n); nt++)
@@ -149,11 +154,20 @@ extern "C" int emu_ku_key_switch(const uint32_t *key_words, const uint32_t *ext 
         for (uint32_t blk = 0; blk < ku::kRing / 16; blk++) {     // builder: 16 coefficients
           uint32_t ab[16];
           for (int c = 0; c < 16; c++) ab[c] = ext[ct * (ku::kRing + 1) + 16 * blk + c] + prec;
-          for (uint32_t s = 0; s < t; s++, st++) {                // one pipeline stage
+          for (uint32_t s = 0; s < spb; s++, st++) {              // one pipeline stage
             uint32_t r[16];
-            for (int c = 0; c < 16; c++) {
-              const uint32_t qb = 16 * s + c, il = qb / t, j = qb % t;
-              r[c] = 1u << ((ab[il] >> (27 - 2 * j)) & 0x18u);
+            if (bb == 2) {
+              for (int c = 0; c < 16; c++) {
+                const uint32_t qb = 16 * s + c, il = qb / t, j = qb % t;
+                r[c] = 1u << ((ab[il] >> (27 - 2 * j)) & 0x18u);
+              }
+            } else {
+              for (uint32_t pp = 0; pp < pps; pp++) {
+                const uint32_t qb = pps * s + pp, il = qb / t, j = qb % t;
+                const uint32_t digit = (ab[il] >> (32 - (j + 1) * bb)) & (P - 1);
+                const uint32_t word = digit >> 2, bit = 1u << ((digit & 3u) * 8);
+                for (uint32_t wq = 0; wq < P / 4; wq++) r[pp * (P / 4) + wq] = (word == wq) ? bit : 0u;
+              }
             }
             const uint8_t *stage = key + ((size_t)nt * nst + st) * ku::kStageBytes;
             for (int ks = 0; ks < 2; ks++)

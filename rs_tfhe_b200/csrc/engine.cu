@@ -139,8 +139,8 @@ int finalize_key(tfhe_engine *e) {
     e->launches++;
   }
   if (ks_variant() == KS_UMMA && ks_umma_supported(e->p.basebit, e->p.iks_t)) {
-    if (!e->kumma) CU(cudaMalloc(reinterpret_cast<void **>(&e->kumma), ks_umma_key_bytes(e->p.n, e->p.iks_t)));
-    CU(ksk_umma_relayout_launch(e->ksk(), e->ksk_stride, e->kumma, e->p.n, e->p.iks_t, e->stream));
+    if (!e->kumma) CU(cudaMalloc(reinterpret_cast<void **>(&e->kumma), ks_umma_key_bytes(e->p.n, e->p.iks_t, e->p.basebit)));
+    CU(ksk_umma_relayout_launch(e->ksk(), e->ksk_stride, e->kumma, e->p.n, e->p.iks_t, e->p.basebit, e->stream));
     e->launches++;
   }
   CU(cudaStreamSynchronize(e->stream));
@@ -160,7 +160,7 @@ int key_switch(tfhe_engine *e, const uint32_t *d_ext, uint32_t *d_out, size_t co
   if (variant == KS_UMMA && e->kumma) {
     KsUmmaArgs k{};
     k.key = e->kumma; k.ext = d_ext; k.out = d_out;
-    k.n = e->p.n; k.iks_t = e->p.iks_t; k.count = count;
+    k.n = e->p.n; k.iks_t = e->p.iks_t; k.basebit = e->p.basebit; k.count = count;
     CU(ks_umma_launch(k, e->stream));
   } else if (e->has_kmma && variant != KS_ROWS) {
     KsMmaArgs k{};

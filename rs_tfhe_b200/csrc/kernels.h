@@ -60,19 +60,19 @@ cudaError_t ks_mma_launch(const KsMmaArgs &args, cudaStream_t stream);
 cudaError_t ksk_mma_relayout_launch(const uint32_t *src_ref, uint32_t *dst, uint32_t n, uint32_t t,
                                     cudaStream_t stream);
 
-// K4 on the tcgen05 tensor cores (keyswitch_umma.cu), gate sets only (basebit == 2, t = 7..9)
+// K4 on the tcgen05 tensor cores (keyswitch_umma.cu): basebit 2..6 (gate sets, UINT1-6)
 struct KsUmmaArgs {
   const uint8_t *key;   // operand tiles, ku_layout.h: [n tile][stage][kstep 2][half 2][240 x 32 B canonical]
   const uint32_t *ext;  // [count][N+1]
   uint32_t *out;        // [count][n+1]
-  uint32_t n, iks_t;
+  uint32_t n, iks_t, basebit;
   size_t count;
 };
 bool ks_umma_supported(uint32_t basebit, uint32_t t);
-size_t ks_umma_key_bytes(uint32_t n, uint32_t t);
+size_t ks_umma_key_bytes(uint32_t n, uint32_t t, uint32_t basebit);
 cudaError_t ks_umma_launch(const KsUmmaArgs &args, cudaStream_t stream);
 cudaError_t ksk_umma_relayout_launch(const uint32_t *blob_rows, uint32_t stride, uint8_t *dst,
-                                     uint32_t n, uint32_t t, cudaStream_t stream);
+                                     uint32_t n, uint32_t t, uint32_t basebit, cudaStream_t stream);
 
 // layout / small kernels (aux.cu)
 cudaError_t bsk_relayout_launch(const double *src_ref, cplx *dst, uint32_t n, uint32_t l2,

@@ -1,5 +1,5 @@
 // keyswitch_umma.cu -- K4 on the 5th-generation tensor cores (tcgen05.mma kind::i8, TMEM
-// accumulators) for the gate parameter sets (basebit = 2, t = 7 / 8 / 9).
+// accumulators) for the parameter sets with basebit 2..6 (gate sets t = 7 / 8 / 9, UINT1-6).
 //
 // Same exact integer GEMM as keyswitch_mma.cu (reference src/trgsw.rs:332-360):
 //   out[ct][x] = (x == n ? b : 0) - sum_{i,j} KSK[i][j][digit_j(a_i + PREC_OFFSET)][x]
@@ -117,9 +117,13 @@ __device__ __forceinline__ void tmem_ld32w(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 
-template <int T>
+template <int BB, int T>
 __global__ void __launch_bounds__(KU_THREADS, 1) ks_umma_kernel(const KsUmmaArgs a) {
-  constexpr uint32_t NST = 64 * T;   // pipeline stages: 1024 * T pairs / 16
+  constexpr int P = 1 << BB;                 // K bytes per (coefficient, digit) pair: one-hot over the digit value
+  constexpr int PPS = ku::kStageK / P;       // pairs per pipeline stage
+  constexpr int SPB = 16 * T / PPS;          // stages per block of 16 coefficients
+  constexpr uint32_t NST = (ku::kRing / 16) * SPB;
+  static_assert(BB >= 2 && BB <= 6 && (16 * T) % PPS == 0, "unsupported key-switch base");
   extern __shared__ __align__(128) uint8_t ku_smem[];
   uint8_t *bst = ku_smem;
   uint32_t *xp = reinterpret_cast<uint32_t *>(ku_smem + KU_BSTAGES * ku::kStageBytes);
@@ -187,7 +191,7 @@ __global__ void __launch_bounds__(KU_THREADS, 1) ks_umma_kernel(const KsUmmaArgs
     __syncwarp();
   } else {
     // ===== A builders: thread = ciphertext row warp*32 + lane =====
-    constexpr uint32_t prec = 1u << (32 - (1 + 2 * T));   // trgsw.rs:338
+    constexpr uint32_t prec = 1u << (32 - (1 + BB * T));   // trgsw.rs:338
     const size_t ct0 = (size_t)mt * ku::kM + (size_t)warp * 32;
     uint32_t *xw = xp + warp * 32 * KU_XPITCH;
     const uint32_t lane_base = tbase + ((uint32_t)(warp * 32) << 16);
@@ -212,16 +216,27 @@ __global__ void __launch_bounds__(KU_THREADS, 1) ks_umma_kernel(const KsUmmaArgs
         uint32_t ab[16];
 #pragma unroll
         for (int c = 0; c < 16; c++) ab[c] = xw[lane * KU_XPITCH + half * 16 + c] + prec;
-        // 16 coefficients x T digits = T stages of 16 pairs; pair 16 s + c = (coefficient il, digit j)
+        // 16 coefficients x T digits = SPB stages of PPS pairs; pair PPS s + pp = (coefficient il, digit j).
+        // One-hot over the digit value k in the pair's P bytes (byte k <-> K index P pair + k); digit 0
+        // meets the zeroed k = 0 key bytes.
 #pragma unroll
-        for (int s = 0; s < T; s++) {
+        for (int s = 0; s < SPB; s++) {
           uint32_t r[16];
+          if (BB == 2) {
 #pragma unroll
-          for (int c = 0; c < 16; c++) {
-            const int qb = 16 * s + c, il = qb / T, j = qb % T;
-            // one-hot over k = 0..3 in the four bytes (byte k <-> K index 4 pair + k); digit 0 meets
-            // the zeroed k = 0 key bytes
-            r[c] = 1u << ((ab[il] >> (27 - 2 * j)) & 0x18u);
+            for (int c = 0; c < 16; c++) {
+              const int qb = 16 * s + c, il = qb / T, j = qb % T;
+              r[c] = 1u << ((ab[il] >> (27 - 2 * j)) & 0x18u);
+            }
+          } else {
+#pragma unroll
+            for (int pp = 0; pp < PPS; pp++) {
+              const int qb = PPS * s + pp, il = qb / T, j = qb % T;
+              const uint32_t digit = (ab[il] >> (32 - (j + 1) * BB)) & (uint32_t)(P - 1);
+              const uint32_t word = digit >> 2, bit = 1u << ((digit & 3u) * 8);
+#pragma unroll
+              for (int wq = 0; wq < P / 4; wq++) r[pp * (P / 4) + wq] = (word == (uint32_t)wq) ? bit : 0u;
+            }
           }
           mbar_wait(&a_empty[as], aph ^ 1);
           tc_fence_after();
@@ -271,49 +286,59 @@ __global__ void __launch_bounds__(KU_THREADS, 1) ks_umma_kernel(const KsUmmaArgs
 // blob KSK rows (u32[rows + 1][stride], reference row order key.rs:102-122) -> operand tiles
 __global__ void ksk_umma_relayout_kernel(const uint32_t *__restrict__ rows, uint32_t stride,
                                          uint32_t *__restrict__ dst, uint32_t n, uint32_t t,
-                                         size_t total) {
+                                         uint32_t basebit, size_t total) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const ku::Src s = ku::decode(idx, t);
+  const ku::Src s = ku::decode(idx, t, basebit);
   uint32_t v = 0;
   if (s.x <= n) {
 #pragma unroll
-    for (uint32_t k = 1; k < 4; k++) {
-      const uint32_t wv = rows[((size_t)s.q * 4 + k) * stride + s.x];
-      v |= ((wv >> (8 * s.plane)) & 0xFFu) << (8 * k);
+    for (uint32_t b = 0; b < 4; b++) {
+      if (s.k0 + b == 0) continue;
+      const uint32_t wv = rows[((size_t)s.row0 + b) * stride + s.x];
+      v |= ((wv >> (8 * s.plane)) & 0xFFu) << (8 * b);
     }
   }
   dst[idx] = v;
 }
 
-template <int T> cudaError_t launch_t(const KsUmmaArgs &args, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(ks_umma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, KU_SMEM);
+template <int BB, int T> cudaError_t launch_t(const KsUmmaArgs &args, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(ks_umma_kernel<BB, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, KU_SMEM);
   if (e != cudaSuccess) return e;
   const size_t mtiles = (args.count + ku::kM - 1) / ku::kM;
   const unsigned grid = (unsigned)(mtiles * ku::n_tiles(args.n));
-  ks_umma_kernel<T><<<grid, KU_THREADS, KU_SMEM, stream>>>(args);
+  ks_umma_kernel<BB, T><<<grid, KU_THREADS, KU_SMEM, stream>>>(args);
   return cudaGetLastError();
 }
 
 }  // namespace
 
-bool ks_umma_supported(uint32_t basebit, uint32_t t) { return basebit == 2 && t >= 7 && t <= 9; }
-size_t ks_umma_key_bytes(uint32_t n, uint32_t t) { return ku::key_words(n, t) * 4; }
+// (basebit, t) of src/params.rs:91-404: gate sets and UINT1 (2; 7/8/9), UINT2 (4; 3), UINT4 (5; 3),
+// UINT3 (6; 2), UINT5/6 (6; 3).  UINT7/8 (basebit 7) stay on the row-walk kernel.
+bool ks_umma_supported(uint32_t basebit, uint32_t t) {
+  return (basebit == 2 && t >= 7 && t <= 9) || (basebit == 4 && t == 3) || (basebit == 5 && t == 3) ||
+         (basebit == 6 && (t == 2 || t == 3));
+}
+size_t ks_umma_key_bytes(uint32_t n, uint32_t t, uint32_t basebit) { return ku::key_words(n, t, basebit) * 4; }
 
 cudaError_t ks_umma_launch(const KsUmmaArgs &args, cudaStream_t stream) {
   if (args.count == 0) return cudaSuccess;
-  switch (args.iks_t) {
-    case 7: return launch_t<7>(args, stream);
-    case 8: return launch_t<8>(args, stream);
-    case 9: return launch_t<9>(args, stream);
+  switch (args.basebit * 16 + args.iks_t) {
+    case 2 * 16 + 7: return launch_t<2, 7>(args, stream);
+    case 2 * 16 + 8: return launch_t<2, 8>(args, stream);
+    case 2 * 16 + 9: return launch_t<2, 9>(args, stream);
+    case 4 * 16 + 3: return launch_t<4, 3>(args, stream);
+    case 5 * 16 + 3: return launch_t<5, 3>(args, stream);
+    case 6 * 16 + 2: return launch_t<6, 2>(args, stream);
+    case 6 * 16 + 3: return launch_t<6, 3>(args, stream);
     default: return cudaErrorInvalidValue;
   }
 }
 
 cudaError_t ksk_umma_relayout_launch(const uint32_t *blob_rows, uint32_t stride, uint8_t *dst,
-                                     uint32_t n, uint32_t t, cudaStream_t stream) {
-  const size_t total = ku::key_words(n, t);
+                                     uint32_t n, uint32_t t, uint32_t basebit, cudaStream_t stream) {
+  const size_t total = ku::key_words(n, t, basebit);
   ksk_umma_relayout_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
-      blob_rows, stride, reinterpret_cast<uint32_t *>(dst), n, t, total);
+      blob_rows, stride, reinterpret_cast<uint32_t *>(dst), n, t, basebit, total);
   return cudaGetLastError();
 }

@@ -192,6 +192,25 @@ def test_other_gate_sets_bit_exact(name):
         e.close()
 
 
+@pytest.mark.parametrize("name", ["uint1", "uint2", "uint3", "uint4", "uint5", "uint7"])
+def test_extract_key_switch_p0_other_bases(name):
+    """Key switch is integer-exact on every parameter set: basebit 2/4/5/6 run on tcgen05.mma
+    (one-hot over 2^basebit digit values), basebit 7 on the row-walk kernel (trgsw.rs:332-360)."""
+    K, ck = keys(name, seed=0x5EED0007)
+    e = T.CudaBootstrap(T.PARAMS_BY_NAME[name], 0)
+    try:
+        e.load_cloud_key(ck)
+        r = np.random.default_rng(11)
+        trlwe = r.integers(0, 2**32, (137, 2, 1024), dtype=np.uint32)   # ragged: one full + one partial M tile
+        trlwe[1] = 0
+        trlwe[2] = 0xFFFFFFFF
+        got = e.batch_extract_key_switch(trlwe)
+        ref = np.stack([K.identity_key_switching(O.sample_extract_index(t[0], t[1], 0)) for t in trlwe])
+        assert np.array_equal(got, ref)
+    finally:
+        e.close()
+
+
 def test_uint4_lut_p2():
     """l=1, Bg=2^22: f64 FFT is inexact and mask words decorrelate, so
     parity is phase-level: equal decryptions and |phase_gpu - phase_oracle| <= 4e-3
