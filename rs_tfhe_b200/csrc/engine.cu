@@ -67,8 +67,8 @@ struct tfhe_engine {
   uint8_t *blob = nullptr;
   cplx *bsk2 = nullptr;   // BSK rows in the TMEM-exchange kernel's thread order (derived, not in the blob)
   uint8_t *kumma = nullptr;  // KSK as tcgen05 operand tiles (derived from the blob's KSK rows; gate sets)
-  size_t blob_bytes = 0, off_ksk = 0, off_kmma = 0, off_tv = 0;
-  bool has_kmma = false;  // basebit == 2: tensor-pipe key switch available
+  size_t blob_bytes = 0, off_ksk = 0, off_tv = 0;
+  uint32_t *kmma = nullptr;  // KSK as mma.sync B fragments (derived; only under TFHE_KS_VARIANT=mma, basebit 2)
   bool key_loaded = false;
   uint32_t decomp_offset = 0;
   uint32_t ksk_rows = 0, ksk_stride = 0;
@@ -89,7 +89,6 @@ struct tfhe_engine {
 
   const cplx *bsk() const { return reinterpret_cast<const cplx *>(blob); }
   const uint32_t *ksk() const { return reinterpret_cast<const uint32_t *>(blob + off_ksk); }
-  const uint32_t *kmma() const { return reinterpret_cast<const uint32_t *>(blob + off_kmma); }
   uint32_t *tv() const { return reinterpret_cast<uint32_t *>(blob + off_tv); }
 };
 
@@ -110,11 +109,8 @@ void blob_layout(tfhe_engine *e) {
   e->ksk_stride = ks_stride(p.n);
   size_t bsk_bytes = (size_t)p.n * 2 * p.l * br::kChunkCplx * sizeof(cplx);
   size_t ksk_bytes = ((size_t)e->ksk_rows + 1) * e->ksk_stride * 4;
-  e->has_kmma = (p.basebit == 2);
-  size_t kmma_bytes = e->has_kmma ? ks_mma_words(p.n, p.iks_t) * 4 : 0;
   e->off_ksk = align_up(bsk_bytes, 256);
-  e->off_kmma = align_up(e->off_ksk + ksk_bytes, 256);
-  e->off_tv = align_up(e->off_kmma + kmma_bytes, 256);
+  e->off_tv = align_up(e->off_ksk + ksk_bytes, 256);
   e->blob_bytes = e->off_tv + (size_t)kMaxLut * 2 * TFHE_N * 4;
 }
 
@@ -143,6 +139,11 @@ int finalize_key(tfhe_engine *e) {
     CU(ksk_umma_relayout_launch(e->ksk(), e->ksk_stride, e->kumma, e->p.n, e->p.iks_t, e->p.basebit, e->stream));
     e->launches++;
   }
+  if (ks_variant() == KS_MMA && e->p.basebit == 2) {
+    if (!e->kmma) CU(cudaMalloc(reinterpret_cast<void **>(&e->kmma), ks_mma_words(e->p.n, e->p.iks_t) * 4));
+    CU(ksk_mma_relayout_launch(e->ksk(), e->ksk_stride, e->kmma, e->p.n, e->p.iks_t, e->stream));
+    e->launches++;
+  }
   CU(cudaStreamSynchronize(e->stream));
   return TFHE_OK;
 }
@@ -162,9 +163,9 @@ int key_switch(tfhe_engine *e, const uint32_t *d_ext, uint32_t *d_out, size_t co
     k.key = e->kumma; k.ext = d_ext; k.out = d_out;
     k.n = e->p.n; k.iks_t = e->p.iks_t; k.basebit = e->p.basebit; k.count = count;
     CU(ks_umma_launch(k, e->stream));
-  } else if (e->has_kmma && variant != KS_ROWS) {
+  } else if (variant == KS_MMA && e->kmma) {
     KsMmaArgs k{};
-    k.w = e->kmma(); k.ext = d_ext; k.out = d_out;
+    k.w = e->kmma; k.ext = d_ext; k.out = d_out;
     k.n = e->p.n; k.iks_t = e->p.iks_t; k.nxg = ks_mma_nxg(e->p.n); k.count = count;
     CU(ks_mma_launch(k, e->stream));
   } else {
@@ -383,6 +384,7 @@ void tfhe_engine_destroy(tfhe_engine *e) {
   if (e->blob) cudaFree(e->blob);
   if (e->bsk2) cudaFree(e->bsk2);
   if (e->kumma) cudaFree(e->kumma);
+  if (e->kmma) cudaFree(e->kmma);
   if (e->tw_a) cudaFree(e->tw_a);
   if (e->tw_b) cudaFree(e->tw_b);
   e->s_misc.release();
@@ -457,12 +459,6 @@ int tfhe_engine_load_cloud_key(tfhe_engine *e, uint32_t decomposition_offset,
                          reinterpret_cast<uint32_t *>(e->blob + e->off_ksk), e->ksk_rows, p.n,
                          e->ksk_stride, e->stream));
   e->launches += 2;
-  if (e->has_kmma) {
-    CU(ksk_mma_relayout_launch(static_cast<const uint32_t *>(e->s_misc.p),
-                               reinterpret_cast<uint32_t *>(e->blob + e->off_kmma), p.n, p.iks_t,
-                               e->stream));
-    e->launches++;
-  }
   CU(cudaMemsetAsync(e->tv(), 0, (size_t)kMaxLut * 2 * TFHE_N * 4, e->stream));
   CU(cudaMemcpyAsync(e->tv(), testvec_a, TFHE_N * 4, cudaMemcpyHostToDevice, e->stream));
   CU(cudaMemcpyAsync(e->tv() + TFHE_N, testvec_b, TFHE_N * 4, cudaMemcpyHostToDevice, e->stream));
@@ -501,11 +497,6 @@ int tfhe_engine_generate_cloud_key(tfhe_engine *e, const uint32_t *s0, const uin
   CU(ksk_relayout_launch(d_ksk_ref, reinterpret_cast<uint32_t *>(e->blob + e->off_ksk), e->ksk_rows,
                          p.n, e->ksk_stride, e->stream));
   e->launches += 4;
-  if (e->has_kmma) {
-    CU(ksk_mma_relayout_launch(d_ksk_ref, reinterpret_cast<uint32_t *>(e->blob + e->off_kmma), p.n,
-                               p.iks_t, e->stream));
-    e->launches++;
-  }
   // key.rs:91-100 (test vector) and :78-89 (decomposition offset)
   std::vector<uint32_t> tv(2 * TFHE_N, 0u);
   for (int x = 0; x < TFHE_N; x++) tv[TFHE_N + x] = 0x20000000u;
@@ -549,6 +540,9 @@ int tfhe_engine_commit_cloud_key(tfhe_engine *e, uint32_t decomposition_offset) 
 }
 
 namespace {
+// Blob format 2: BSK | KSK rows | test-vector slots (format 1 also carried the mma.sync fragment copy
+// of the KSK, now derived on demand like the other kernel-specific key orders).
+constexpr uint32_t kBlobFormat = 2;
 struct BlobHeader {
   char magic[8];
   uint32_t version, n, N, l, bgbit, basebit, iks_t, decomposition_offset, n_lut, reserved;
@@ -570,7 +564,7 @@ int tfhe_engine_export_cloud_key(tfhe_engine *e, void *host_buf, size_t bytes) {
   CU(cudaSetDevice(e->dev));
   BlobHeader hd{};
   memcpy(hd.magic, "TFHEB200", 8);
-  hd.version = TFHE_B200_ABI_VERSION;
+  hd.version = kBlobFormat;
   hd.n = e->p.n; hd.N = e->p.N; hd.l = e->p.l; hd.bgbit = e->p.bgbit; hd.basebit = e->p.basebit;
   hd.iks_t = e->p.iks_t; hd.decomposition_offset = e->decomp_offset; hd.n_lut = (uint32_t)e->n_lut;
   hd.payload_bytes = e->blob_bytes;
@@ -586,7 +580,7 @@ int tfhe_engine_import_cloud_key(tfhe_engine *e, const void *host_buf, size_t by
   if (bytes < sizeof(BlobHeader)) return fail(TFHE_ERR_INVALID, "truncated blob");
   BlobHeader hd;
   memcpy(&hd, host_buf, sizeof(hd));
-  if (memcmp(hd.magic, "TFHEB200", 8) != 0 || hd.version != TFHE_B200_ABI_VERSION)
+  if (memcmp(hd.magic, "TFHEB200", 8) != 0 || hd.version != kBlobFormat)
     return fail(TFHE_ERR_INVALID, "not a tfhe_b200 key blob (or wrong version)");
   const tfhe_params &p = e->p;
   if (hd.n != p.n || hd.N != p.N || hd.l != p.l || hd.bgbit != p.bgbit || hd.basebit != p.basebit ||

@@ -151,11 +151,12 @@ __global__ void __launch_bounds__(KM_WARPS * 32, KM_CTAS_DEF) ks_mma_kernel(cons
     }
 }
 
-// caller's KSK rows (key.rs:102-122) -> B-fragment order.
+// blob KSK rows (u32[rows + 1][stride], reference row order key.rs:102-122) -> B-fragment order.
 // dst index = ((((iblk*t + j)*8 + ii)*nxg + xg)*8 + g8)*4 + p ; value byte k = byte p of
 // KSK[((8*iblk+ii)*t + j)*4 + k][8*xg + g8]  (k = 0 forced to 0: never selected)
-__global__ void ksk_mma_relayout_kernel(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst,
-                                        uint32_t n, uint32_t t, uint32_t nxg, size_t total) {
+__global__ void ksk_mma_relayout_kernel(const uint32_t *__restrict__ src, uint32_t stride,
+                                        uint32_t *__restrict__ dst, uint32_t n, uint32_t t, uint32_t nxg,
+                                        size_t total) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const uint32_t p = idx & 3, g8 = (idx >> 2) & 7;
@@ -170,7 +171,7 @@ __global__ void ksk_mma_relayout_kernel(const uint32_t *__restrict__ src, uint32
     const size_t row0 = ((size_t)i * t + j) * 4;
 #pragma unroll
     for (uint32_t k = 1; k < 4; k++) {
-      const uint32_t wv = src[(row0 + k) * (n + 1) + x];
+      const uint32_t wv = src[(row0 + k) * stride + x];
       v |= ((wv >> (8 * p)) & 0xFFu) << (8 * k);
     }
   }
@@ -193,10 +194,10 @@ cudaError_t ks_mma_launch(const KsMmaArgs &args, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
-cudaError_t ksk_mma_relayout_launch(const uint32_t *src_ref, uint32_t *dst, uint32_t n, uint32_t t,
-                                    cudaStream_t stream) {
+cudaError_t ksk_mma_relayout_launch(const uint32_t *blob_rows, uint32_t stride, uint32_t *dst, uint32_t n,
+                                    uint32_t t, cudaStream_t stream) {
   const size_t total = ks_mma_words(n, t);
-  ksk_mma_relayout_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src_ref, dst, n, t,
+  ksk_mma_relayout_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(blob_rows, stride, dst, n, t,
                                                                               ks_mma_nxg(n), total);
   return cudaGetLastError();
 }
