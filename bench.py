@@ -395,6 +395,20 @@ def main():
             "clocks": clocks,
             "key_load_s": key_load_s, "key_broadcast_ms": key_bcast_ms,
         }
+        # secondary kernel: the key switch as an exact u8 GEMM on tcgen05.mma (1-2 % of the step).
+        # Algorithmic ops = 2 x (N t 2^basebit one-hot columns) x ((n+1) x 4 byte planes) per gate; the
+        # peak is int8 = 2 x the measured dense bf16 rate of MEASURED_PEAKS.json (same tensor datapath).
+        try:
+            bf16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+            tsrc = "2 x MEASURED_PEAKS.json bf16_tflops"
+        except Exception:
+            bf16, tsrc = 2250.0, "2 x nominal dense bf16 (B200_PROFILING.md fallback)"
+        ks_ops = 2.0 * (N * P.iks_t * (1 << P.basebit)) * (w * 4) * count
+        ks_ach = ks_ops / (ks_avg * 1e-3) / 1e12
+        line["roofline_key_switch"] = {
+            "kernel": "ks_umma_kernel", "bound": "tensor", "achieved": ks_ach, "peak": 2.0 * bf16,
+            "unit": "TOP/s", "frac": ks_ach / (2.0 * bf16), "peak_source": tsrc,
+            "algorithmic_ops_per_launch": ks_ops}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_leg(args.params, args.cpu_sample, engine=eng)
         _emit(line)

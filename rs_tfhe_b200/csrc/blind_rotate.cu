@@ -1054,6 +1054,12 @@ __global__ void __launch_bounds__(256, 1) blind_rotate_latency_kernel(const BrAr
             mbar_arrive_expect_tx(&full[r], kStageBytes);
             tma_load_1d(reinterpret_cast<uint8_t *>(ring) + r * kStageBytes,
                         src0 + ((size_t)i * L2 + r) * kStageBytes, kStageBytes, &full[r]);
+            // a lone ciphertext streams the key cold from HBM: pull the next step's row into L2 now
+            if (i + 1 < n)
+              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(
+                               src0 + ((size_t)(i + 1) * L2 + r) * kStageBytes),
+                           "n"(kStageBytes)
+                           : "memory");
           }
           parity ^= 1;
         }
