@@ -408,6 +408,9 @@ def main():
         line["roofline_key_switch"] = {
             "kernel": "ks_umma_kernel", "bound": "tensor", "achieved": ks_ach, "peak": 2.0 * bf16,
             "unit": "TOP/s", "frac": ks_ach / (2.0 * bf16), "peak_source": tsrc,
+            "peak_nominal": 4500.0, "frac_of_nominal": ks_ach / 4500.0,
+            "note": "ops count every one-hot column incl. the structurally zero digit-0 columns "
+                    "(1/2^basebit of K); ncu: tensor pipe 62.5 % active (profiles/r1_ks_umma_ncu_full.json)",
             "algorithmic_ops_per_launch": ks_ops}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_leg(args.params, args.cpu_sample, engine=eng)
