@@ -12,12 +12,12 @@ import rs_tfhe_b200 as T
 from rs_tfhe_b200.client import Client, SecretKey
 
 count = int(sys.argv[1]) if len(sys.argv) > 1 else 1024          # BASELINE configs[0]
-sk = SecretKey.new(T.SECURITY_128_BIT, seed=1)
+sk = SecretKey.new(T.SECURITY_128_BIT)
 engine = T.CudaBootstrap(T.SECURITY_128_BIT, 0)
 t = time.perf_counter()
-engine.generate_cloud_key(sk.key_lv0, sk.key_lv1, seed=2)          # CloudKey::new, on the device
+engine.generate_cloud_key(sk.key_lv0, sk.key_lv1)                 # CloudKey::new, on the device
 print(f"cloud key generated on the GPU in {(time.perf_counter() - t) * 1e3:.1f} ms")
-client = Client(sk, seed=3)
+client = Client(sk)
 a = np.array([i % 2 == 0 for i in range(count)])                   # batch_gates_scaling.rs:11
 b = np.array([i % 3 == 0 for i in range(count)])
 inputs = np.stack([client.encrypt_bool(a), client.encrypt_bool(b)], axis=1)

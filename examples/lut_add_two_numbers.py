@@ -18,10 +18,10 @@ args = [x for x in sys.argv[1:] if not x.startswith("--")]
 a, b = (int(args[0]), int(args[1])) if len(args) >= 2 else (42, 137)   # lut_add_two_numbers.rs:52-54
 P = T.SECURITY_128_BIT if "--gate-params" in sys.argv else T.SECURITY_UINT5
 m = 32
-sk = SecretKey.new(P, seed=11)
+sk = SecretKey.new(P)
 engine = T.CudaBootstrap(P, 0)
-engine.generate_cloud_key(sk.key_lv0, sk.key_lv1, seed=12)
-client = Client(sk, seed=13)
+engine.generate_cloud_key(sk.key_lv0, sk.key_lv1)
+client = Client(sk)
 gen = T.Generator(m, engine)
 lut_low = gen.generate_lookup_table(lambda x: x % 16)                   # sum nibble
 lut_carry = gen.generate_lookup_table(lambda x: 1 if x >= 16 else 0)    # carry

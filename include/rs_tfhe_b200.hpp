@@ -15,6 +15,7 @@
 // byte.  There is no CPU fallback: without a CUDA device construction throws.
 #pragma once
 #include <cmath>
+#include <cstring>
 #include <cstdint>
 #include <functional>
 #include <memory>
@@ -68,6 +69,24 @@ inline void check(int rc) {
   if (rc != TFHE_OK) throw std::runtime_error(std::string("tfhe_b200: ") + tfhe_last_error());
 }
 
+// Identity of a CloudKey's CONTENT (not its address: a new key at a reused address, or a mutated
+// key, must be re-uploaded).  FNV-1a over the offset, the sizes and 1024 strided samples of each of
+// the three arrays -- microseconds per call, and any regenerated key differs in every sample.
+inline uint64_t cloud_key_fingerprint(const CloudKey &ck) {
+  uint64_t h = 1469598103934665603ull;
+  auto mix = [&h](uint64_t v) { for (int i = 0; i < 8; i++) { h ^= (v >> (8 * i)) & 0xff; h *= 1099511628211ull; } };
+  mix(ck.decomposition_offset); mix(ck.key_switching_key.size()); mix(ck.bootstrapping_key.size());
+  for (int i = 0; i < TFHE_N; i += 8) { mix(ck.blind_rotate_testvec.a[i]); mix(ck.blind_rotate_testvec.b[i]); }
+  const size_t ks = ck.key_switching_key.size(), bs = ck.bootstrapping_key.size();
+  for (size_t i = 0; i < 1024 && ks; i++) mix(ck.key_switching_key[(i * 2654435761ull) % ks]);
+  for (size_t i = 0; i < 1024 && bs; i++) {
+    uint64_t bits;
+    std::memcpy(&bits, &ck.bootstrapping_key[(i * 2654435761ull) % bs], 8);
+    mix(bits);
+  }
+  return h;
+}
+
 enum class Gate : int { Nand = 0, And, Or, Xor, Xnor, Nor, AndNy, AndYn, OrNy, OrYn };
 
 // bootstrap::Bootstrap (bootstrap/mod.rs:23-38)
@@ -79,10 +98,26 @@ class Bootstrap {
   virtual const char *name() const = 0;
 };
 
-// lut::LookupTable (lut/lookup_table.rs:16-19): poly.a == 0, poly.b = table; lives on the device
+// lut::LookupTable (lut/lookup_table.rs:16-19): poly.a == 0, poly.b = table; lives on the device.
+// Move-only owner of its device slot: dropping it releases the slot, as dropping the reference's
+// LookupTable frees its polynomial.
 struct LookupTable {
   std::vector<Torus> poly_b;
   int lut_id = -1;
+  tfhe_engine *engine = nullptr;
+  LookupTable() = default;
+  LookupTable(const LookupTable &) = delete;
+  LookupTable &operator=(const LookupTable &) = delete;
+  LookupTable(LookupTable &&o) noexcept : poly_b(std::move(o.poly_b)), lut_id(o.lut_id), engine(o.engine) { o.lut_id = -1; }
+  LookupTable &operator=(LookupTable &&o) noexcept {
+    if (this != &o) { release(); poly_b = std::move(o.poly_b); lut_id = o.lut_id; engine = o.engine; o.lut_id = -1; }
+    return *this;
+  }
+  ~LookupTable() { release(); }
+  void release() {
+    if (lut_id > 0 && engine) tfhe_lut_release(engine, lut_id);   // a stale id (key reloaded) is refused, not fatal
+    lut_id = -1;
+  }
   bool is_empty() const {
     for (Torus v : poly_b) if (v) return false;
     return true;
@@ -106,11 +141,13 @@ class CudaBootstrap final : public Bootstrap {
   tfhe_engine *raw() { return e_; }
 
   void bind(const CloudKey &ck) {
-    if (&ck == bound_) return;
+    const uint64_t fp = cloud_key_fingerprint(ck);
+    if (have_key_ && fp == bound_fp_) return;
     check(tfhe_engine_load_cloud_key(e_, ck.decomposition_offset, ck.blind_rotate_testvec.a,
                                      ck.blind_rotate_testvec.b, ck.key_switching_key.data(),
                                      ck.bootstrapping_key.data()));
-    bound_ = &ck;
+    bound_fp_ = fp;
+    have_key_ = true;
   }
 
   Ciphertext bootstrap(const Ciphertext &ctxt, const CloudKey &ck) override {  // vanilla.rs:40-52
@@ -158,7 +195,22 @@ class CudaBootstrap final : public Bootstrap {
     LookupTable lut;
     lut.poly_b.resize(TFHE_N);
     check(tfhe_lut_generate(e_, table.data(), message_modulus, scale, lut.poly_b.data(), &lut.lut_id));
+    lut.engine = e_;
     return lut;
+  }
+  // LutBootstrap::bootstrap_func over a batch (bootstrap/lut.rs:49-65): table generated into the
+  // engine's scratch slot, nothing to release, callable without bound
+  std::vector<Ciphertext> batch_bootstrap_func(const std::vector<Ciphertext> &cts,
+                                               const std::function<size_t(size_t)> &f,
+                                               uint32_t message_modulus, const CloudKey &ck) {
+    bind(ck);
+    std::vector<Torus> table(message_modulus);
+    for (uint32_t x = 0; x < message_modulus; x++) table[x] = static_cast<Torus>(f(x) % message_modulus);
+    const size_t w = params_.n + 1;
+    std::vector<Torus> in(cts.size() * w), out(cts.size() * w);
+    for (size_t i = 0; i < cts.size(); i++) std::copy(cts[i].p.begin(), cts[i].p.end(), in.begin() + i * w);
+    check(tfhe_batch_bootstrap_func(e_, table.data(), message_modulus, 0.0, in.data(), out.data(), cts.size()));
+    return unpack(out, cts.size());
   }
   // LutBootstrap::bootstrap_lut over a batch (bootstrap/lut.rs:79-99)
   std::vector<Ciphertext> batch_bootstrap_lut(const std::vector<Ciphertext> &cts, const LookupTable &lut,
@@ -180,7 +232,8 @@ class CudaBootstrap final : public Bootstrap {
   }
   SecurityParams params_;
   tfhe_engine *e_ = nullptr;
-  const CloudKey *bound_ = nullptr;
+  uint64_t bound_fp_ = 0;
+  bool have_key_ = false;
 };
 
 // gates::Gates (gates.rs:30-218)
@@ -242,8 +295,7 @@ class LutBootstrap {
   const char *name() const { return "lut"; }
   Ciphertext bootstrap_func(const Ciphertext &ct, const std::function<size_t(size_t)> &f,
                             uint32_t message_modulus, const CloudKey &ck) {  // lut.rs:49-65
-    auto lut = e_->generate_lookup_table(f, message_modulus, ck);
-    return bootstrap_lut(ct, lut, ck);
+    return e_->batch_bootstrap_func({ct}, f, message_modulus, ck)[0];
   }
   Ciphertext bootstrap_lut(const Ciphertext &ct, const LookupTable &lut, const CloudKey &ck) {  // lut.rs:79-99
     return e_->batch_bootstrap_lut({ct}, lut, ck)[0];

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define TFHE_B200_ABI_VERSION 1
+#define TFHE_B200_ABI_VERSION 2
 #define TFHE_N 1024 /* params::trgsw_lv1::N -- fixed in the reference (params.rs:391) */
 
 typedef enum {
@@ -69,7 +69,7 @@ typedef enum {
   TFHE_GATE_COUNT = 10
 } tfhe_gate;
 
-typedef struct tfhe_engine tfhe_engine; /* opaque; one per (process, GPU) */
+typedef struct tfhe_engine tfhe_engine; /* opaque; one per (process, GPU), or per GPU set (create_multi) */
 
 /* ---- library ------------------------------------------------------------ */
 int tfhe_abi_version(void);
@@ -82,6 +82,21 @@ int tfhe_device_count(void);
  * (bootstrap/mod.rs:41-43, vanilla.rs:28-31) -- the strategy object a Gates
  * instance owns (gates.rs:30-45).  device_id is the CUDA ordinal. */
 int tfhe_engine_create(const tfhe_params *params, int device_id, tfhe_engine **out);
+/* One engine over several GPUs of this process.  The reference's batch entry points
+ * parallelise with `par_map` over ciphertexts (trgsw.rs:297-305, gates.rs:352-383); here every
+ * host-buffer batch call on the returned engine shards its ciphertexts over the devices in
+ * contiguous index ranges [r*count/G, (r+1)*count/G), one host thread and one stream set per GPU,
+ * with no per-gate communication.  The single collective is the cloud key: tfhe_engine_load_cloud_key
+ * / _generate_cloud_key / _import_cloud_key upload and re-lay out on device_ids[0] and ncclBroadcast
+ * the re-laid-out blob to the others over NVLink (NCCL is resolved at run time; n_devices == 1 needs
+ * none).  LUT tables are kept identical on all devices.  The *_dev entry points and
+ * tfhe_engine_cloud_key_blob address device_ids[0] only. */
+int tfhe_engine_create_multi(const tfhe_params *params, const int *device_ids, int n_devices,
+                             tfhe_engine **out);
+/* number of GPUs the engine spans */
+int tfhe_engine_device_count(const tfhe_engine *e);
+/* device time (ms, CUDA events) of the last cloud-key ncclBroadcast; 0 for a one-GPU engine */
+int tfhe_engine_last_broadcast_ms(tfhe_engine *e, float *ms_out);
 void tfhe_engine_destroy(tfhe_engine *e);
 /* Run all engine work on `cuda_stream` (a cudaStream_t; NULL restores the
  * engine's own stream).  Lets a host runtime order engine calls with its own. */
@@ -110,9 +125,13 @@ int tfhe_engine_load_cloud_key(tfhe_engine *e, uint32_t decomposition_offset,
 /* Replaces: key::CloudKey::new(&SecretKey) (src/key.rs:59-66: gen_key_switching_key :102-122 +
  * gen_bootstrapping_key :128-156, TRGSW encryption trgsw.rs:29-68) ON THE DEVICE.
  * s0 = SecretKey.key_lv0 (n words of 0/1), s1 = key_lv1 (N words); alpha_lv0 = KSK_ALPHA,
- * alpha_lv1 = BSK_ALPHA (params.rs:468-469).  The reference's RNG is unseeded, so the key is not
- * comparable bit for bit; it is generated with Philox4x32-10 from `seed` directly in the device
- * layout.  The test vector and decomposition offset are the standard ones (key.rs:78-100). */
+ * alpha_lv1 = BSK_ALPHA (params.rs:468-469).  The reference's RNG is unseeded (rand::thread_rng, an
+ * OS-seeded ChaCha generator), so the key is not comparable bit for bit; masks and noise come from
+ * the ChaCha20 block function under a 256-bit key, straight into the device layout.
+ *   seed == 0  : the key is drawn from OS entropy (getentropy) -- the ONLY setting for real keys;
+ *   seed != 0  : key expanded from `seed`, reproducible, for tests and benches; INSECURE (the
+ *                published masks of the key-switching key would let a 2^64 search recover it).
+ * The test vector and decomposition offset are the standard ones (key.rs:78-100). */
 int tfhe_engine_generate_cloud_key(tfhe_engine *e, const uint32_t *s0, const uint32_t *s1,
                                    double alpha_lv0, double alpha_lv1, uint64_t seed);
 /* Multi-GPU: the device-resident, re-laid-out key is one contiguous blob.  Rank
@@ -158,10 +177,22 @@ int tfhe_lut_generate(tfhe_engine *e, const uint32_t *f_table, uint32_t modulus,
 /* Register a caller-made test vector (LookupTable::from_poly, lookup_table.rs:33). */
 int tfhe_lut_register(tfhe_engine *e, const uint32_t *poly_a /*[N] or NULL => 0*/,
                       const uint32_t *poly_b /*[N]*/, int *lut_id_out);
+/* Drop a table made by tfhe_lut_generate / tfhe_lut_register (dropping a lookup_table::LookupTable,
+ * lookup_table.rs:16-19): its device slot is reused by later tables.  An engine holds at most 62
+ * live tables.  Table ids are opaque; ids from before the latest cloud-key load are rejected
+ * (TFHE_ERR_INVALID), never resolved to another table.  Id 0 is the cloud key's own test vector. */
+int tfhe_lut_release(tfhe_engine *e, int lut_id);
 /* Replaces: LutBootstrap::bootstrap_lut (bootstrap/lut.rs:79-99) over a batch;
  * bootstrap_func (lut.rs:49-65) = tfhe_lut_generate + this. */
 int tfhe_batch_bootstrap_lut(tfhe_engine *e, int lut_id, const uint32_t *in /*[count][n+1]*/,
                              uint32_t *out /*[count][n+1]*/, size_t count);
+/* Replaces: LutBootstrap::bootstrap_func (bootstrap/lut.rs:49-65) over a batch in ONE call: the
+ * table of f (f_table[x] = f(x), x < modulus; scale <= 0 => 1/(2*modulus)) is generated on the
+ * device into a scratch slot that every call overwrites, so -- like the reference, which builds
+ * and drops a LookupTable per call -- it can be called without bound and holds no table id. */
+int tfhe_batch_bootstrap_func(tfhe_engine *e, const uint32_t *f_table, uint32_t modulus, double scale,
+                              const uint32_t *in /*[count][n+1]*/, uint32_t *out /*[count][n+1]*/,
+                              size_t count);
 /* Same with a per-ciphertext table (lut_ids[count]): independent LUT bootstraps of one circuit
  * level -- e.g. the sum and carry tables of examples/lut_add_two_numbers.rs:138,147, which read
  * the same input -- go out as ONE batch instead of one call per table. */
@@ -171,6 +202,18 @@ int tfhe_batch_bootstrap_lut_multi(tfhe_engine *e, const int32_t *lut_ids /*[cou
  * (trgsw.rs:332-360, trlwe.rs:106-120) on caller-supplied TRLWE samples. */
 int tfhe_batch_extract_key_switch(tfhe_engine *e, const uint32_t *in_trlwe /*[count][2][N]*/,
                                   uint32_t *out /*[count][n+1]*/, size_t count);
+
+/* ---- the FFT seam: trait FFTProcessor (src/fft/mod.rs:80-107; active implementation
+ *      KlemsaProcessor, src/fft/klemsa.rs:88-174) over batches, on the same device passes the
+ *      blind rotation uses.  Layouts are the reference's: a polynomial is u32[N]; a spectrum is
+ *      f64[N] = re[0..N/2) | im[0..N/2), natural bin order, values = 2 x the twisted DFT. ---- */
+/* Replaces: FFTProcessor::batch_ifft::<1024> / ifft (fft/mod.rs:84,99-101; klemsa.rs:88-117). */
+int tfhe_batch_ifft(tfhe_engine *e, const uint32_t *in /*[count][N]*/, double *out /*[count][N]*/, size_t count);
+/* Replaces: FFTProcessor::batch_fft::<1024> / fft (fft/mod.rs:89,104-106; klemsa.rs:119-150). */
+int tfhe_batch_fft(tfhe_engine *e, const double *in /*[count][N]*/, uint32_t *out /*[count][N]*/, size_t count);
+/* Replaces: FFTProcessor::poly_mul::<1024> (fft/mod.rs:93; klemsa.rs:152-174): a*b mod X^N+1. */
+int tfhe_batch_poly_mul(tfhe_engine *e, const uint32_t *a /*[count][N]*/, const uint32_t *b /*[count][N]*/,
+                        uint32_t *out /*[count][N]*/, size_t count);
 
 /* ---- next to the path: LWE proxy re-encryption = the key-switch kernel with the
  *      level-0 dimension as input ------------------------------------------------------ */

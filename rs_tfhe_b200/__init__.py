@@ -126,6 +126,9 @@ def _load():
     L.tfhe_last_error.restype = C.c_char_p
     L.tfhe_device_count.restype = C.c_int
     L.tfhe_engine_create.argtypes = [C.POINTER(_CParams), C.c_int, C.POINTER(vp)]
+    L.tfhe_engine_create_multi.argtypes = [C.POINTER(_CParams), C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    L.tfhe_engine_device_count.argtypes = [vp]
+    L.tfhe_engine_last_broadcast_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.tfhe_engine_destroy.argtypes = [vp]
     L.tfhe_engine_destroy.restype = None
     L.tfhe_engine_set_stream.argtypes = [vp, vp]
@@ -142,6 +145,11 @@ def _load():
     L.tfhe_batch_blind_rotate.argtypes = [vp, u32p, u32p, C.c_size_t]
     L.tfhe_lut_generate.argtypes = [vp, u32p, C.c_uint32, C.c_double, u32p, C.POINTER(C.c_int)]
     L.tfhe_lut_register.argtypes = [vp, u32p, u32p, C.POINTER(C.c_int)]
+    L.tfhe_batch_ifft.argtypes = [vp, u32p, vp, C.c_size_t]
+    L.tfhe_batch_fft.argtypes = [vp, vp, u32p, C.c_size_t]
+    L.tfhe_batch_poly_mul.argtypes = [vp, u32p, u32p, u32p, C.c_size_t]
+    L.tfhe_lut_release.argtypes = [vp, C.c_int]
+    L.tfhe_batch_bootstrap_func.argtypes = [vp, u32p, C.c_uint32, C.c_double, u32p, u32p, C.c_size_t]
     L.tfhe_batch_bootstrap_lut.argtypes = [vp, C.c_int, u32p, u32p, C.c_size_t]
     L.tfhe_batch_extract_key_switch.argtypes = [vp, u32p, u32p, C.c_size_t]
     L.tfhe_batch_bootstrap_lut_multi.argtypes = [vp, vp, u32p, u32p, C.c_size_t]
@@ -158,7 +166,7 @@ def _load():
     L.tfhe_engine_import_cloud_key.argtypes = [vp, vp, C.c_size_t]
     L.tfhe_engine_generate_cloud_key.argtypes = [vp, u32p, u32p, C.c_double, C.c_double, C.c_uint64]
     L.tfhe_probe_fp64_tflops.argtypes = [vp, C.POINTER(C.c_double)]
-    if L.tfhe_abi_version() != 1:
+    if L.tfhe_abi_version() != 2:
         raise EngineError("libtfhe_b200.so ABI version mismatch")
     _lib = L
     return L
@@ -210,14 +218,29 @@ class CudaBootstrap:
     (process, GPU).  Unlike the CPU strategies it keeps the cloud key resident on the
     device, so the key is bound with `load_cloud_key` instead of passed per call."""
 
-    def __init__(self, params: SecurityParams = SECURITY_128_BIT, device: int = 0):
+    def __init__(self, params: SecurityParams = SECURITY_128_BIT, device=0):
+        """`device`: one CUDA ordinal, or a sequence of ordinals for one engine over several GPUs
+        (batches are sharded over them; the cloud key is broadcast with NCCL at load time)."""
         L = _load()
         self.params = params
         self._h = C.c_void_p()
         cp = _CParams(params.n, params.N, params.l, params.bgbit, params.basebit, params.iks_t)
-        _check(L.tfhe_engine_create(C.byref(cp), device, C.byref(self._h)))
+        if np.ndim(device) == 0:
+            _check(L.tfhe_engine_create(C.byref(cp), int(device), C.byref(self._h)))
+        else:
+            ids = (C.c_int * len(device))(*[int(d) for d in device])
+            _check(L.tfhe_engine_create_multi(C.byref(cp), ids, len(device), C.byref(self._h)))
         self._key: Optional[CloudKey] = None
         self.device = device
+
+    @property
+    def n_devices(self) -> int:
+        return int(_load().tfhe_engine_device_count(self._h))
+
+    def last_broadcast_ms(self) -> float:
+        ms = C.c_float(0.0)
+        _check(_load().tfhe_engine_last_broadcast_ms(self._h, C.byref(ms)))
+        return float(ms.value)
 
     def close(self) -> None:
         if getattr(self, "_h", None) and self._h.value:
@@ -245,9 +268,10 @@ class CudaBootstrap:
             _ptr(_u32(ck.blind_rotate_testvec_b)), _ptr(ksk), _ptr(bsk)))
         self._key = ck
 
-    def generate_cloud_key(self, key_lv0, key_lv1, seed: int) -> None:
+    def generate_cloud_key(self, key_lv0, key_lv1, seed: int = 0) -> None:
         """key::CloudKey::new(&secret_key) (src/key.rs:59-66) on the device: KSK + Fourier BSK are
-        generated straight into the device layout (Philox4x32-10 keyed by `seed`)."""
+        generated straight into the device layout by a ChaCha20-based generator.  seed=0 (default)
+        keys it from OS entropy; a non-zero seed gives a reproducible, INSECURE key (tests only)."""
         p = self.params
         s0, s1 = _u32(key_lv0, (p.n,)), _u32(key_lv1, (N,))
         _check(_load().tfhe_engine_generate_cloud_key(self._h, _ptr(s0), _ptr(s1), p.alpha_lv0,
@@ -360,6 +384,31 @@ class CudaBootstrap:
         _check(_load().tfhe_batch_extract_key_switch(self._h, _ptr(t), _ptr(out), t.shape[0]))
         return out
 
+    # ---- FFTProcessor seam (src/fft/mod.rs:80-107)
+    def batch_ifft(self, polys) -> np.ndarray:
+        """FFTProcessor::batch_ifft::<1024>: u32[count][N] -> f64[count][N] (re | im, 2 x DFT)."""
+        x = _u32(polys, (N,)).reshape(-1, N)
+        out = np.empty((x.shape[0], N), dtype=np.float64)
+        _check(_load().tfhe_batch_ifft(self._h, _ptr(x), _ptr(out), x.shape[0]))
+        return out
+
+    def batch_fft(self, spectra) -> np.ndarray:
+        """FFTProcessor::batch_fft::<1024>: f64[count][N] -> u32[count][N]."""
+        f = np.ascontiguousarray(spectra, dtype=np.float64).reshape(-1, N)
+        out = np.empty((f.shape[0], N), dtype=np.uint32)
+        _check(_load().tfhe_batch_fft(self._h, _ptr(f), _ptr(out), f.shape[0]))
+        return out
+
+    def batch_poly_mul(self, a, b) -> np.ndarray:
+        """FFTProcessor::poly_mul::<1024> over a batch: a*b mod X^N+1."""
+        a = _u32(a, (N,)).reshape(-1, N)
+        b = _u32(b, (N,)).reshape(-1, N)
+        if a.shape != b.shape:
+            raise ValueError("a and b must have the same shape")
+        out = np.empty_like(a)
+        _check(_load().tfhe_batch_poly_mul(self._h, _ptr(a), _ptr(b), _ptr(out), a.shape[0]))
+        return out
+
     # ---- LUT
     def lut_generate(self, f_table: Sequence[int], modulus: int, scale: float = 0.0):
         f = _u32(list(f_table))
@@ -375,6 +424,28 @@ class CudaBootstrap:
         a = None if poly_a is None else _u32(poly_a, (N,))
         _check(_load().tfhe_lut_register(self._h, _ptr(a), _ptr(_u32(poly_b, (N,))), C.byref(lut_id)))
         return lut_id.value
+
+    def lut_release(self, lut_id: int) -> None:
+        """Give a table's device slot back (dropping a LookupTable)."""
+        _check(_load().tfhe_lut_release(self._h, int(lut_id)))
+
+    def batch_bootstrap_func(self, f_table: Sequence[int], modulus: int, ctxt, scale: float = 0.0,
+                             cloud_key: Optional[CloudKey] = None):
+        """LutBootstrap::bootstrap_func (bootstrap/lut.rs:49-65) over a batch in one call: the
+        table is generated into a scratch slot, so no table id is held and the call can be
+        repeated without bound."""
+        self._bind(cloud_key)
+        f = _u32(list(f_table))
+        if f.shape != (modulus,):
+            raise ValueError("f_table must have `modulus` entries")
+        w = self.params.n + 1
+        cts = _u32(ctxt, (w,))
+        single = cts.ndim == 1
+        cts = cts.reshape(-1, w)
+        out = np.empty_like(cts)
+        _check(_load().tfhe_batch_bootstrap_func(self._h, _ptr(f), modulus, scale, _ptr(cts), _ptr(out),
+                                                 cts.shape[0]))
+        return out[0] if single else out
 
     def batch_bootstrap_lut(self, lut_id, ctxt, cloud_key: Optional[CloudKey] = None):
         """LutBootstrap::bootstrap_lut over a batch; `lut_id` may be one id or one id per
@@ -606,6 +677,19 @@ class LookupTable:
     def is_empty(self) -> bool:
         return not self.poly_b.any()
 
+    def release(self) -> None:
+        """Free the device slot (the reference's LookupTable is dropped by scope)."""
+        if self.lut_id > 0:
+            self.engine.lut_release(self.lut_id)
+            self.lut_id = -1
+
+    def __del__(self):
+        try:
+            if self.lut_id > 0 and getattr(self.engine, "_h", None) and self.engine._h.value:
+                self.engine.lut_release(self.lut_id)
+        except Exception:
+            pass
+
 
 class Generator:
     """lut::Generator (src/lut/generator.rs:16-262); tables are generated on the device."""
@@ -638,9 +722,9 @@ class LutBootstrap:
 
     def bootstrap_func(self, ct_in, f: Callable[[int], int], message_modulus: int,
                        cloud_key: Optional[CloudKey] = None):
-        self.engine._bind(cloud_key)   # LUT slots live beside the key on the device
-        lut = Generator(message_modulus, self.engine).generate_lookup_table(f)
-        return self.bootstrap_lut(ct_in, lut, cloud_key)
+        m = message_modulus
+        table = [int(f(x)) % m for x in range(m)]   # the closure is tabulated host-side
+        return self.engine.batch_bootstrap_func(table, m, ct_in, 0.0, cloud_key)
 
     def bootstrap_lut(self, ct_in, lut: LookupTable, cloud_key: Optional[CloudKey] = None):
         return self.engine.batch_bootstrap_lut(lut.lut_id, ct_in, cloud_key)

@@ -6,10 +6,15 @@ are -- but a Python caller needs them to drive the engine end to end (see exampl
   TLWELv0::encrypt_f64 / encrypt_bool src/tlwe.rs:37-58   (+ utils::gaussian_f64, utils.rs:22-38)
   TLWELv0::decrypt_bool               src/tlwe.rs:60-68
   encrypt_lwe_message / decrypt_lwe_message   src/tlwe.rs:84-126
-The reference draws from an unseeded thread_rng; here the generator is numpy's, seeded by the caller.
+The reference draws from rand::thread_rng (an OS-seeded ChaCha generator).  Here the default
+(seed=None) draws every key bit, mask word and noise sample from the operating system's CSPRNG
+(os.urandom); passing a seed switches to numpy's PCG64, which is reproducible and NOT
+cryptographically secure -- for tests and benches only (the mask words of a ciphertext are public,
+and a non-cryptographic generator's state can be recovered from them).
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -23,6 +28,32 @@ def _f64_to_torus(d: np.ndarray) -> np.ndarray:
     return np.trunc(t).astype(np.int64).astype(np.uint32)
 
 
+class _OsRng:
+    """The subset of numpy's Generator interface used below, backed by os.urandom."""
+
+    def integers(self, low, high, size, dtype=np.uint32):
+        shape = (size,) if np.isscalar(size) else tuple(size)
+        count = int(np.prod(shape))
+        raw = np.frombuffer(os.urandom(4 * count), dtype=np.uint32).reshape(shape)
+        span = int(high) - int(low)
+        if span == 2**32:
+            return raw.astype(dtype)
+        if span & (span - 1):
+            raise ValueError("power-of-two ranges only")
+        return ((raw & np.uint32(span - 1)) + np.uint32(low)).astype(dtype)
+
+    def normal(self, mean, sigma, size):
+        count = int(np.prod((size,) if np.isscalar(size) else tuple(size)))
+        u = np.frombuffer(os.urandom(16 * count), dtype=np.uint64).reshape(2, count)
+        a = ((u[0] >> np.uint64(11)).astype(np.float64) + 0.5) * (1.0 / 9007199254740992.0)
+        b = ((u[1] >> np.uint64(11)).astype(np.float64) + 0.5) * (1.0 / 9007199254740992.0)
+        return mean + sigma * np.sqrt(-2.0 * np.log(a)) * np.cos(2.0 * np.pi * b)   # Box-Muller
+
+
+def _rng(seed):
+    return _OsRng() if seed is None else np.random.default_rng(seed)
+
+
 @dataclass
 class SecretKey:
     """key::SecretKey (src/key.rs:21-48): uniform binary level-0 and level-1 keys."""
@@ -32,7 +63,7 @@ class SecretKey:
 
     @staticmethod
     def new(params: SecurityParams = SECURITY_128_BIT, seed: int | None = None) -> "SecretKey":
-        r = np.random.default_rng(seed)
+        r = _rng(seed)
         return SecretKey(params, r.integers(0, 2, params.n, dtype=np.uint32),
                          r.integers(0, 2, N, dtype=np.uint32))
 
@@ -42,7 +73,7 @@ class Client:
 
     def __init__(self, sk: SecretKey, seed: int | None = None):
         self.sk = sk
-        self.rng = np.random.default_rng(seed)
+        self.rng = _rng(seed)
 
     def encrypt_f64(self, mu, alpha: float | None = None) -> np.ndarray:
         """tlwe.rs:37-53 over a batch: a uniform, b = <a,s> + f64_to_torus(N(0,alpha)) + f64_to_torus(mu)."""

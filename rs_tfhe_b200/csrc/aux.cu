@@ -1,5 +1,6 @@
 // aux.cu -- key re-layout at upload, device-side LUT generation, sample extraction.
 #include "kernels.h"
+#include "brs_core.cuh"
 
 namespace {
 
@@ -32,6 +33,19 @@ __global__ void bsk_permute_kernel(const cplx *__restrict__ src, cplx *__restric
   const cplx v = src[(idx & ~(size_t)63) + 8 * k0 + k1];
   const bool neg = ((idx >> 7) & 1) && ((T >> 4) & 1);   // idx = ((row * 8 + k2) * 2 + o) * 64 + T
   dst[idx] = neg ? br::mk(-v.x, -v.y) : v;
+}
+
+// Device-order key rows -> the order of the 128-thread kernel (blind_rotate_s.cu): slot T of a
+// (kd, o) slice holds bin brs::bin_of(T, kd); the standard order keeps bin k0 + 8 k1 + 64 k2 in slot
+// 8 k0 + k1 of slice (k2, o).
+__global__ void bsk_permute_s_kernel(const cplx *__restrict__ src, cplx *__restrict__ dst, size_t total) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // ((row * 4 + kd) * 2 + o) * 128 + T
+  if (idx >= total) return;
+  const int T = idx & 127, o = (idx >> 7) & 1, kd = (idx >> 8) & 3;
+  const size_t row = idx >> 10;
+  const int k = brs::bin_of(T, kd);
+  const int k0 = k & 7, k1 = (k >> 3) & 7, k2 = k >> 6;
+  dst[idx] = src[((row * 8 + k2) * 2 + o) * 64 + 8 * k0 + k1];
 }
 
 // Reference KSK image (key.rs:102-122: u32[N*t*2^basebit][n+1]) -> rows padded to
@@ -120,6 +134,12 @@ cudaError_t bsk_relayout_launch(const double *src_ref, cplx *dst, uint32_t n, ui
 cudaError_t bsk_permute_launch(const cplx *src, cplx *dst, size_t rows, cudaStream_t stream) {
   const size_t total = rows * br::kChunkCplx;
   bsk_permute_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src, dst, total);
+  return cudaGetLastError();
+}
+
+cudaError_t bsk_permute_s_launch(const cplx *src, cplx *dst, size_t rows, cudaStream_t stream) {
+  const size_t total = rows * brs::kRowCplx;
+  bsk_permute_s_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src, dst, total);
   return cudaGetLastError();
 }
 

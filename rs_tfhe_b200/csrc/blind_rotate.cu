@@ -26,7 +26,7 @@ using namespace br;
 #define BR_PRODUCER_SLEEP_NS 256
 #endif
 #ifndef BR_DEFAULT_VARIANT
-#define BR_DEFAULT_VARIANT 8
+#define BR_DEFAULT_VARIANT 9
 #endif
 
 namespace {
@@ -1268,7 +1268,7 @@ int br_variant() {
   if (v < 0) {
     const char *e = getenv("TFHE_BR_VARIANT");
     v = e ? atoi(e) : BR_DEFAULT_VARIANT;
-    if (v < 1 || v > 8) v = BR_DEFAULT_VARIANT;
+    if (v < 1 || v > 9) v = BR_DEFAULT_VARIANT;
   }
   return v;
 }
@@ -1287,7 +1287,9 @@ template <int L, int BGBIT>
 cudaError_t launch_t(const BrArgs &args, int num_sms, cudaStream_t stream) {
   if (L > 1 && args.count <= (size_t)br_latency_threshold(num_sms))
     return launch_latency<L, BGBIT>(args, num_sms, stream);
-  // 8 (default): pass B<->C exchange through tensor memory + one shuffle stage (permuted key layout)
+  // 9 (default): 128 threads per ciphertext, all-FMA radix 4/8/4/4 passes (blind_rotate_s.cu)
+  if (br_variant() == 9) return br_launch_s(L, BGBIT, args, num_sms, stream);
+  // 8: 64 threads per ciphertext, pass B<->C exchange through tensor memory + one shuffle stage (permuted key layout)
   if (br_variant() == 8) return launch_x<L, BGBIT, true>(args, num_sms, stream);
   // 7: variant 3 with the 2^52-bias conversions
   if (br_variant() == 7) return launch_v<L, BGBIT, 4, 4, 3, true, 232, 40, false, true>(args, num_sms, stream);
@@ -1306,6 +1308,7 @@ cudaError_t launch_t(const BrArgs &args, int num_sms, cudaStream_t stream) {
 }  // namespace
 
 bool br_uses_permuted_key() { return br_variant() == 8; }
+bool br_uses_s_key() { return br_variant() == 9; }
 
 bool br_supported(uint32_t l, uint32_t bgbit) {
   return (l == 3 && bgbit == 6) || (l == 2 && bgbit == 10) || (l == 1 && bgbit == 18) ||

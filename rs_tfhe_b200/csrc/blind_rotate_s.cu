@@ -1,0 +1,294 @@
+// blind_rotate_s.cu -- K0+K3, throughput shape: persistent blind rotation with 128 threads per
+// ciphertext (16 FP64 warps per SM, 4 per sub-partition).
+//
+// Replaces (reference, file:line under rs-tfhe):
+//   gates.rs:366-373 (batch prep), trgsw.rs:198-274 (blind_rotate[_with_testvec]),
+//   trgsw.rs:174-196 (cmux), :77-142 (external product), :144-171 (decomposition),
+//   :307-330 (X^k), fft/klemsa.rs:88-150 (transforms), trlwe.rs:106-136 (extract).
+//
+// One persistent CTA per SM owns 4 ciphertexts at a time; ciphertext g is walked through the n CMUX
+// steps by warps 4g..4g+3, one on each SM sub-partition, so every sub-partition always holds four
+// FP64 warps in four independent phases (the 64-thread shape of round 1 held two and left the FP64
+// pipe idle 37 % of the cycles).  Per thread: 4 complex points of the transform in flight and
+// 2 x 4 complex MAC accumulators (brs_core.cuh has the index maps and the all-FMA butterflies).
+// Data movement of one transform:
+//   pass A -> B   shared memory (crosses warps); pass B is the split radix-8: both lanes of a pair
+//                 read the same 8 inputs (broadcast) and each produces 4 outputs
+//   pass B -> C, C -> D and back   TENSOR MEMORY, inside each warp: tcgen05.st.32x32b.x16 (thread =
+//                 TMEM lane, 16 columns = 4 complex) + two tcgen05.ld.16x256b.x2 swap the two register
+//                 index bits with lane bits (4,3) and rotate the other lane bits up by two; no barrier,
+//                 no shared-memory traffic, no shuffles
+//   pass B' -> A' shared memory (padded rows); A' is the split radix-8 of the inverse
+// The Fourier-domain key streams through a ring of 16 KB stages filled by 1-D TMA bulk copies
+// (cp.async.bulk + mbarrier complete_tx) issued by a producer warp; a stage is released when all 16
+// consumer warps have used it, so each key row crosses L2->SM once per CTA per step.
+// Per-thread transform constants (20 complex) live in tensor memory next to the exchange blocks.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "br_ptx.cuh"
+#include "brs_core.cuh"
+#include "brs_tmem.cuh"
+#include "kernels.h"
+
+using namespace br;
+using namespace brp;
+using namespace brt;
+
+namespace {
+
+constexpr int kStageBytes = brs::kRowCplx * 16;   // 16 KB: one key row
+constexpr int kG = 4;                             // ciphertexts resident per CTA
+constexpr int kConsumers = kG * brs::kT;          // 512 threads
+constexpr int kThreads = kConsumers + 128;        // + a producer warpgroup (one warp per sub-partition)
+// Register plan.  A sub-partition's file holds 512 registers per lane and hosts 4 consumer warps + 1 warp of
+// the producer warpgroup.  setmaxnreg only moves registers inside the CTA's LAUNCH allocation
+// (5 warps x 96 = 480 per lane: the largest multiple-of-8 count that fits), so consumers can grow to
+// (480 - 24) / 4 = 114 -> 112.  (Asking for 120 blocks forever: measured, the kernel hangs.)
+constexpr int kRegsCons = 112, kRegsProd = 24;
+
+#ifdef TFHE_S_ABLATION_BUILD
+__device__ unsigned long long g_trace[16 * 4 * 16];   // [warp][step 100..103][point]
+#define TRACE(pt)                                                                              \
+  if ((ABL & 8) && blockIdx.x == 0 && rd == 0 && i >= 100 && i < 104 && lane == 0)             \
+    g_trace[(warp * 4 + (i - 100)) * 16 + (pt)] = clock64();
+#else
+#define TRACE(pt)
+#endif
+
+template <int L, int BGBIT, int STAGES, bool MAGIC, int ABL = 0>
+__global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel_s(const BrArgs args) {
+  constexpr int L2 = 2 * L;
+  constexpr bool EXACT = (L == 3 && BGBIT == 6);
+  constexpr int kAccBytes = 2 * kN * 4;
+  constexpr int kInvBytes = 8 * brs::kInvPitch * 16;                    // one output's inverse exchange buffer
+  constexpr int kFwdBytes = kHalf * 16;                                  // one digit's forward exchange buffer
+  constexpr int kExchBytes = (L * kFwdBytes > 2 * kInvBytes) ? L * kFwdBytes : 2 * kInvBytes;
+  constexpr int kAbarBytes = 2432;
+  constexpr int kGroupBytes = kAccBytes + kExchBytes + kAbarBytes;
+  extern __shared__ __align__(128) uint8_t smem[];
+  cplx *ring = reinterpret_cast<cplx *>(smem);
+  uint8_t *groups = smem + STAGES * kStageBytes;
+  uint64_t *full = reinterpret_cast<uint64_t *>(groups + kG * kGroupBytes);
+  uint64_t *empty = full + STAGES;
+  uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(empty + STAGES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t n = args.n;
+  const uint32_t grid = gridDim.x;
+  const uint32_t rounds = (uint32_t)((args.count + (size_t)grid * kG - 1) / ((size_t)grid * kG));
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4 * kG); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_base_s)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tbase = *tmem_base_s;
+  if (warp >= 4 * kG) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProd));
+    if (warp == 4 * kG && lane == 0) {
+      // ===== producer: stream key rows (i, r) in the kernel's thread order =====
+      const uint8_t *src0 = reinterpret_cast<const uint8_t *>(args.bsk3);
+      uint32_t stage = 0, parity = 0;
+      const uint32_t rows = n * L2;
+      for (uint32_t rd = 0; rd < rounds; rd++)
+        for (uint32_t row = 0; row < rows; row++) {
+          mbar_wait_backoff(&empty[stage], parity ^ 1, 128);
+          mbar_arrive_expect_tx(&full[stage], kStageBytes);
+          tma_load_1d(reinterpret_cast<uint8_t *>(ring) + stage * kStageBytes, src0 + (size_t)row * kStageBytes,
+                      kStageBytes, &full[stage]);
+          if (++stage == STAGES) { stage = 0; parity ^= 1; }
+        }
+    }
+    return;
+  }
+  // ===== consumers: warps 4g..4g+3 own ciphertext g of the round =====
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsCons));
+  const int g = warp >> 2;
+  const int T = threadIdx.x & (brs::kT - 1);
+  uint8_t *gbase = groups + g * kGroupBytes;
+  uint32_t *acc = reinterpret_cast<uint32_t *>(gbase);
+  cplx *exch = reinterpret_cast<cplx *>(gbase + kAccBytes);
+  uint16_t *abar_s = reinterpret_cast<uint16_t *>(gbase + kAccBytes + kExchBytes);
+  // TMEM columns of this warp: 5 blocks of 16 (constants), then two exchange blocks
+  const uint32_t taddr = tbase + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)g * 128u;
+  const uint32_t t_b = taddr, t_cd = taddr + 16, t_cbi = taddr + 32, t_ai = taddr + 48, t_ut = taddr + 64;
+  const uint32_t tq0 = taddr + 80, tq1 = taddr + 96;
+  {
+    const cplx *tw = args.tw_s + (size_t)T * brs::kTwPerThread;
+#pragma unroll
+    for (int blk = 0; blk < 5; blk++) {
+      cplx t[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) t[k] = tw[4 * blk + k];
+      tm_store4(taddr + 16 * blk, t);
+    }
+    tm_wait_st();
+  }
+  // De-phase the four ciphertexts of the CTA: a sub-partition hosts one warp of each, and four warps in
+  // the same phase leave the FP64 pipe idle whenever they all reach an integer / exchange stretch together.
+  if (args.stagger) {
+    const long long until = clock64() + (long long)args.stagger * g;
+    while (clock64() < until) __nanosleep(64);
+  }
+  uint32_t stage = 0, parity = 0;
+  for (uint32_t rd = 0; rd < rounds; rd++) {
+    const size_t ct = ((size_t)rd * kG + g) * grid + blockIdx.x;
+    const bool active = ct < args.count;
+    if (active) prologue<brs::kT>(args, ct, T, abar_s, acc);
+    named_sync<brs::kT>(g + 1);
+    for (uint32_t i = 0; i < n; i++) {
+      if (active) {
+        cplx racc[2][4];
+        TRACE(0)
+        const uint32_t abar = abar_s[i];
+#pragma unroll
+        for (int o = 0; o < 2; o++)
+#pragma unroll
+          for (int k = 0; k < 4; k++) racc[o][k] = mk(0.0, 0.0);
+#pragma unroll 1
+        for (int p = 0; p < 2; p++) {
+          {
+            uint32_t t_re[4], t_im[4];
+            brs::load_t(T, acc + p * kN, abar, args.offset, t_re, t_im);
+#pragma unroll
+            for (int d = 0; d < L; d++) brs::fwd_pass_a<BGBIT, MAGIC>(T, d, t_re, t_im, exch + d * kHalf);
+          }
+          TRACE(1 + 5 * p)
+          named_sync<brs::kT>(g + 1);
+          TRACE(2 + 5 * p)
+#pragma unroll
+          for (int d = 0; d < L; d++) {
+            cplx y[4];
+            {
+              cplx tb[4];
+              if (ABL & 2) { for (int k = 0; k < 4; k++) tb[k] = mk(0.5 + T * 1e-3, 0.25 + k); } else tm_load4(t_b, tb);
+              brs::fwd_pass_b(T, exch + d * kHalf, tb[0], tb[1], tb[2], y);
+            }
+            if (!(ABL & 1)) xchg_fwd(tq0, y);
+            cplx tcd[4];
+            if (ABL & 2) { for (int k = 0; k < 4; k++) tcd[k] = mk(0.5 + T * 1e-3, 0.25 + k); } else tm_load4(t_cd, tcd);
+            brs::r4<false>(y, tcd[0], tcd[1]);
+            if (!(ABL & 1)) xchg_fwd(tq1, y);
+            brs::r4<false>(y, tcd[2], tcd[3]);
+            mbar_wait(&full[stage], parity);
+            const cplx *row = ring + stage * brs::kRowCplx + T;
+#pragma unroll
+            for (int kd = 0; kd < 4; kd++) {
+              if (ABL & 4) {   // no key reads from shared memory
+                cfma(racc[0][kd], y[kd], mk(0.5 + kd, 1e-3 * T));
+                cfma(racc[1][kd], y[kd], mk(0.25 + kd, 2e-3 * T));
+              } else {
+                cfma(racc[0][kd], y[kd], row[(kd * 2 + 0) * brs::kT]);
+                cfma(racc[1][kd], y[kd], row[(kd * 2 + 1) * brs::kT]);
+              }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+            if (++stage == STAGES) { stage = 0; parity ^= 1; }
+            if (d == 0) { TRACE(3 + 5 * p) }
+          }
+          TRACE(4 + 5 * p)
+          named_sync<brs::kT>(g + 1);   // everyone has read this polynomial's pass-A output
+          TRACE(5 + 5 * p)
+        }
+        {
+          cplx ti[4];
+          tm_load4(t_cbi, ti);
+#pragma unroll
+          for (int o = 0; o < 2; o++) {
+            brs::r4_plain<true>(racc[o]);
+            if (!(ABL & 1)) xchg_inv(tq0, racc[o]);
+            brs::r4<true>(racc[o], ti[0], ti[1]);
+            if (!(ABL & 1)) xchg_inv(tq1, racc[o]);
+            brs::r4<true>(racc[o], ti[2], ti[3]);
+            brs::inv_store_b(T, racc[o], exch + o * (8 * brs::kInvPitch));
+          }
+        }
+        TRACE(11)
+        named_sync<brs::kT>(g + 1);
+        TRACE(12)
+        {
+          cplx ta[4], ut[4];
+          tm_load4(t_ai, ta);
+          tm_load4(t_ut, ut);
+#pragma unroll
+          for (int o = 0; o < 2; o++)
+            brs::inv_pass_a<EXACT, MAGIC>(T, exch + o * (8 * brs::kInvPitch), ta[0], ta[1], ta[2], ut, acc + o * kN);
+        }
+        TRACE(13)
+        named_sync<brs::kT>(g + 1);
+        TRACE(14)
+      } else {
+        // idle group: keep the ring's phase accounting in lock step
+        for (int c = 0; c < L2; c++) {
+          mbar_wait(&full[stage], parity);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; parity ^= 1; }
+        }
+      }
+    }
+    if (active) epilogue<brs::kT>(args, ct, T, acc);
+    named_sync<brs::kT>(g + 1);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  asm volatile("bar.sync 15, %0;" ::"n"(kConsumers) : "memory");
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tbase));
+}
+
+template <int L, int BGBIT, int STAGES>
+cudaError_t launch_s(const BrArgs &args_in, int num_sms, cudaStream_t stream) {
+  constexpr bool MAGIC = (L == 3 && BGBIT == 6);
+  if (!args_in.bsk3 || !args_in.tw_s) return cudaErrorInvalidValue;   // engine did not build this kernel's key order
+  BrArgs args = args_in;
+  static const int stagger = [] { const char *e = getenv("TFHE_S_STAGGER"); return e ? atoi(e) : 0; }();
+  args.stagger = (uint32_t)stagger;
+  static const int abl = [] { const char *e = getenv("TFHE_S_ABLATE"); return e ? atoi(e) : 0; }();
+  auto kern = blind_rotate_kernel_s<L, BGBIT, STAGES, MAGIC>;
+#ifdef TFHE_S_ABLATION_BUILD
+  if (L == 3 && STAGES == 4) {
+    if (abl == 1) kern = blind_rotate_kernel_s<L, BGBIT, STAGES, MAGIC, 1>;
+    if (abl == 2) kern = blind_rotate_kernel_s<L, BGBIT, STAGES, MAGIC, 2>;
+    if (abl == 3) kern = blind_rotate_kernel_s<L, BGBIT, STAGES, MAGIC, 3>;
+    if (abl == 4) kern = blind_rotate_kernel_s<L, BGBIT, STAGES, MAGIC, 4>;
+    if (abl == 7) kern = blind_rotate_kernel_s<L, BGBIT, STAGES, MAGIC, 7>;
+    if (abl == 8) kern = blind_rotate_kernel_s<L, BGBIT, STAGES, MAGIC, 8>;
+  }
+#endif
+  (void)abl;
+  constexpr int kInvBytes = 8 * brs::kInvPitch * 16, kFwdBytes = kHalf * 16;
+  constexpr int kExchBytes = (L * kFwdBytes > 2 * kInvBytes) ? L * kFwdBytes : 2 * kInvBytes;
+  const int smem = STAGES * kStageBytes + kG * (2 * kN * 4 + kExchBytes + 2432) + 2 * STAGES * 8 + 16;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  int grid = (int)(args.count < (size_t)num_sms ? args.count : (size_t)num_sms);
+  if (grid < 1) grid = 1;
+  kern<<<grid, kThreads, smem, stream>>>(args);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+#ifdef TFHE_S_ABLATION_BUILD
+extern "C" int tfhe_debug_read_trace(unsigned long long *out) {
+  return (int)cudaMemcpyFromSymbol(out, g_trace, sizeof(g_trace));
+}
+#endif
+
+cudaError_t br_launch_s(uint32_t l, uint32_t bgbit, const BrArgs &args, int num_sms, cudaStream_t stream) {
+  if (args.count == 0) return cudaSuccess;
+  static const int stages = [] { const char *e = getenv("TFHE_S_STAGES"); return e ? atoi(e) : 4; }();
+  if (l == 3 && bgbit == 6) return stages == 5 ? launch_s<3, 6, 5>(args, num_sms, stream) : launch_s<3, 6, 4>(args, num_sms, stream);
+  if (l == 2 && bgbit == 10) return launch_s<2, 10, 4>(args, num_sms, stream);
+  if (l == 1 && bgbit == 18) return launch_s<1, 18, 4>(args, num_sms, stream);
+  if (l == 1 && bgbit == 22) return launch_s<1, 22, 4>(args, num_sms, stream);
+  if (l == 1 && bgbit == 23) return launch_s<1, 23, 4>(args, num_sms, stream);
+  return cudaErrorInvalidValue;
+}

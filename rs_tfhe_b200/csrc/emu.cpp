@@ -106,6 +106,133 @@ extern "C" int emu_blind_rotate(uint32_t n, uint32_t l, uint32_t bgbit, uint32_t
   return 0;
 }
 
+// ---- 128-thread kernel (blind_rotate_s.cu / brs_core.cuh) ----------------------------------------
+// Tensor memory is modelled per warp as rows x value slots with the access shapes the kernel uses:
+//   forward exchange  tcgen05.st.32x32b.x16 (lane l' writes slot s to row l')  then two
+//                     tcgen05.ld.16x256b.x2 (lane l reads value 2H+h from row 16H + (l>>2) + 8h, slot l&3)
+//   inverse exchange  the mirror image (st.16x256b.x2, ld.32x32b.x16)
+// (shapes verified on hardware by tools/probe/tmem_xchg_probe.cu).
+#include "brs_core.cuh"
+
+namespace {
+
+struct WarpTmem { cplx v[32][4]; };
+
+void emu_xchg_fwd(cplx (*y)[4] /*[128][4]*/) {
+  for (int W = 0; W < 4; W++) {
+    WarpTmem tm;
+    for (int l = 0; l < 32; l++)
+      for (int s = 0; s < 4; s++) tm.v[l][s] = y[32 * W + l][s];
+    for (int l = 0; l < 32; l++)
+      for (int H = 0; H < 2; H++)
+        for (int h = 0; h < 2; h++) y[32 * W + l][2 * H + h] = tm.v[16 * H + (l >> 2) + 8 * h][l & 3];
+  }
+}
+void emu_xchg_inv(cplx (*u)[4]) {
+  for (int W = 0; W < 4; W++) {
+    WarpTmem tm;
+    for (int l = 0; l < 32; l++)
+      for (int H = 0; H < 2; H++)
+        for (int h = 0; h < 2; h++) tm.v[16 * H + (l >> 2) + 8 * h][l & 3] = u[32 * W + l][2 * H + h];
+    for (int l = 0; l < 32; l++)
+      for (int s = 0; s < 4; s++) u[32 * W + l][s] = tm.v[l][s];
+  }
+}
+
+template <int L, int BGBIT, bool EXACT>
+void run_s(uint32_t n, uint32_t offset, const double *bsk_ref, const uint32_t *tv, const uint32_t *lwe,
+           int steps, uint32_t *out) {
+  constexpr int L2 = 2 * L;
+  constexpr int kT = brs::kT;
+  std::vector<uint32_t> acc(2 * kN);
+  std::vector<cplx> exch(L * kHalf > 2 * 8 * brs::kInvPitch ? L * kHalf : 2 * 8 * brs::kInvPitch);
+  std::vector<cplx> row(L2 * brs::kRowCplx);
+  static cplx tw[kT][brs::kTwPerThread];
+  static cplx racc[kT][2][4];
+  static cplx y[kT][4];
+  for (int t = 0; t < kT; t++) brs::make_tw(t, tw[t]);
+
+  uint32_t b_tilda = (uint32_t)(2 * kN - (((uint64_t)lwe[n] + (1u << 20)) >> 21));
+  for (int o = 0; o < 2; o++)
+    for (int j = 0; j < kN; j++) acc[o * kN + j] = rot_coeff(tv + o * kN, j, b_tilda);
+
+  uint32_t count = steps < 0 ? n : (uint32_t)steps;
+  for (uint32_t i = 0; i < count; i++) {
+    // upload permutation of BSK[i] (same index math as bsk_permute_s_kernel)
+    for (int r = 0; r < L2; r++)
+      for (int kd = 0; kd < 4; kd++)
+        for (int o = 0; o < 2; o++)
+          for (int t = 0; t < kT; t++) {
+            const double *src = bsk_ref + (((size_t)i * L2 + r) * 2 + o) * kN;
+            int k = brs::bin_of(t, kd);
+            row[r * brs::kRowCplx + brs::row_index(kd, o, t)] =
+                mk(src[k] * (1.0 / 1024.0), src[k + kHalf] * (1.0 / 1024.0));
+          }
+    uint32_t abar = (uint32_t)(lwe[i] + (1u << 20)) >> 21;
+    memset(racc, 0, sizeof(racc));
+    static uint32_t t_re[kT][4], t_im[kT][4];
+    for (int p = 0; p < 2; p++) {
+      for (int t = 0; t < kT; t++) brs::load_t(t, acc.data() + p * kN, abar, offset, t_re[t], t_im[t]);
+      for (int d = 0; d < L; d++)
+        for (int t = 0; t < kT; t++)
+          brs::fwd_pass_a<BGBIT, false>(t, d, t_re[t], t_im[t], exch.data() + d * kHalf);
+      for (int d = 0; d < L; d++) {
+        for (int t = 0; t < kT; t++)
+          brs::fwd_pass_b(t, exch.data() + d * kHalf, tw[t][brs::TW_B], tw[t][brs::TW_B + 1],
+                          tw[t][brs::TW_B + 2], y[t]);
+        emu_xchg_fwd(y);
+        for (int t = 0; t < kT; t++) brs::r4<false>(y[t], tw[t][brs::TW_C], tw[t][brs::TW_C + 1]);
+        emu_xchg_fwd(y);
+        for (int t = 0; t < kT; t++) brs::r4<false>(y[t], tw[t][brs::TW_D], tw[t][brs::TW_D + 1]);
+        const cplx *rw = row.data() + (p * L + d) * brs::kRowCplx;
+        for (int t = 0; t < kT; t++)
+          for (int kd = 0; kd < 4; kd++) {
+            cfma(racc[t][0][kd], y[t][kd], rw[brs::row_index(kd, 0, t)]);
+            cfma(racc[t][1][kd], y[t][kd], rw[brs::row_index(kd, 1, t)]);
+          }
+      }
+    }
+    for (int o = 0; o < 2; o++) {
+      for (int t = 0; t < kT; t++) { brs::r4_plain<true>(racc[t][o]); for (int k = 0; k < 4; k++) y[t][k] = racc[t][o][k]; }
+      emu_xchg_inv(y);
+      for (int t = 0; t < kT; t++) brs::r4<true>(y[t], tw[t][brs::TW_CI], tw[t][brs::TW_CI + 1]);
+      emu_xchg_inv(y);
+      for (int t = 0; t < kT; t++) brs::r4<true>(y[t], tw[t][brs::TW_BI], tw[t][brs::TW_BI + 1]);
+      for (int t = 0; t < kT; t++) brs::inv_store_b(t, y[t], exch.data() + o * (8 * brs::kInvPitch));
+    }
+    for (int o = 0; o < 2; o++)
+      for (int t = 0; t < kT; t++) {
+        cplx ut[4];
+        for (int k = 0; k < 4; k++) ut[k] = tw[t][brs::TW_UT + k];
+        brs::inv_pass_a<EXACT, false>(t, exch.data() + o * (8 * brs::kInvPitch), tw[t][brs::TW_AI],
+                                      tw[t][brs::TW_AI + 1], tw[t][brs::TW_AI + 2], ut, acc.data() + o * kN);
+      }
+  }
+  memcpy(out, acc.data(), 2 * kN * sizeof(uint32_t));
+}
+
+}  // namespace
+
+extern "C" int emu_blind_rotate_s(uint32_t n, uint32_t l, uint32_t bgbit, uint32_t offset,
+                                  const double *bsk_ref, const uint32_t *tv, const uint32_t *lwe,
+                                  int steps, uint32_t *out_trlwe) {
+  if (l == 3 && bgbit == 6) run_s<3, 6, true>(n, offset, bsk_ref, tv, lwe, steps, out_trlwe);
+  else if (l == 2 && bgbit == 10) run_s<2, 10, false>(n, offset, bsk_ref, tv, lwe, steps, out_trlwe);
+  else if (l == 1 && bgbit == 18) run_s<1, 18, false>(n, offset, bsk_ref, tv, lwe, steps, out_trlwe);
+  else if (l == 1 && bgbit == 22) run_s<1, 22, false>(n, offset, bsk_ref, tv, lwe, steps, out_trlwe);
+  else if (l == 1 && bgbit == 23) run_s<1, 23, false>(n, offset, bsk_ref, tv, lwe, steps, out_trlwe);
+  else return -1;
+  return 0;
+}
+// the twiddle table the engine uploads (cplx[128][20] as doubles)
+extern "C" void emu_s_twiddles(double *out) {
+  for (int t = 0; t < brs::kT; t++) {
+    cplx tw[brs::kTwPerThread];
+    brs::make_tw(t, tw);
+    for (int k = 0; k < brs::kTwPerThread; k++) { out[(t * brs::kTwPerThread + k) * 2] = tw[k].x; out[(t * brs::kTwPerThread + k) * 2 + 1] = tw[k].y; }
+  }
+}
+
 // ---- model of the tcgen05 key switch (keyswitch_umma.cu) -----------------------------------
 // Same index arithmetic as the device code (ku_layout.h): emu_ku_build_key is the relayout
 // kernel; emu_ku_key_switch walks CTA tiles, pipeline stages, K steps and accumulator halves as the

@@ -10,9 +10,16 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <string>
+#include <thread>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h>
+#include <unistd.h>
+
 #include "kernels.h"
+#include "brs_core.cuh"
 
 #ifndef TFHE_KS_DEFAULT
 #define TFHE_KS_DEFAULT 0   // 0 = tcgen05 (umma), 1 = mma.sync, 2 = row walk
@@ -38,7 +45,9 @@ int fail(int code, const char *fmt, ...) {
                   __FILE__, __LINE__);                                               \
   } while (0)
 
-constexpr int kMaxLut = 64;          // test-vector slots (slot 0 = cloud-key test vector)
+constexpr int kMaxLut = 64;          // test-vector slots (slot 0 = cloud-key test vector,
+                                     // slot kMaxLut-1 = scratch of the ephemeral bootstrap_func path)
+constexpr int kScratchLut = kMaxLut - 1;
 constexpr size_t kChunk = 1u << 17;  // ciphertexts per internal pass (bounds scratch memory)
 
 struct Scratch {
@@ -66,13 +75,18 @@ struct tfhe_engine {
   // cloud key: one contiguous device blob = BSK | KSK | test-vector slots
   uint8_t *blob = nullptr;
   cplx *bsk2 = nullptr;   // BSK rows in the TMEM-exchange kernel's thread order (derived, not in the blob)
+  cplx *bsk3 = nullptr;   // BSK rows in the 128-thread kernel's order (derived, not in the blob)
+  cplx *tw_s = nullptr;   // per-thread constants of the 128-thread kernel
   uint8_t *kumma = nullptr;  // KSK as tcgen05 operand tiles (derived from the blob's KSK rows; gate sets)
   size_t blob_bytes = 0, off_ksk = 0, off_tv = 0;
   uint32_t *kmma = nullptr;  // KSK as mma.sync B fragments (derived; only under TFHE_KS_VARIANT=mma, basebit 2)
   bool key_loaded = false;
   uint32_t decomp_offset = 0;
   uint32_t ksk_rows = 0, ksk_stride = 0;
-  int n_lut = 1;
+  // LUT ids handed out = (key epoch << 8) | slot, so ids from before a key (re)load are rejected;
+  // id 0 is always the cloud-key test vector.
+  bool lut_used[kMaxLut] = {true};
+  uint32_t key_epoch = 0;
   cplx *tw_a = nullptr, *tw_b = nullptr;
   Scratch s_misc;
   // two pipeline slots: H2D of chunk k+1 and D2H of chunk k-1 overlap the kernels of chunk k
@@ -86,6 +100,12 @@ struct tfhe_engine {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float last_ms[2] = {0.f, 0.f};
   uint64_t launches = 0;
+  // multi-GPU (tfhe_engine_create_multi): this engine is device_ids[0]; peers are the other devices'
+  // engines, owned here.  The cloud key is broadcast root -> peers with NCCL at key-load time; batch
+  // calls shard contiguous index ranges over all of them, one host thread per GPU.
+  std::vector<tfhe_engine *> peers;
+  void *nccl_comms = nullptr;   // ncclComm_t[1 + peers.size()]
+  float last_broadcast_ms = 0.f;
 
   const cplx *bsk() const { return reinterpret_cast<const cplx *>(blob); }
   const uint32_t *ksk() const { return reinterpret_cast<const uint32_t *>(blob + off_ksk); }
@@ -134,6 +154,12 @@ int finalize_key(tfhe_engine *e) {
     CU(bsk_permute_launch(e->bsk(), e->bsk2, rows, e->stream));
     e->launches++;
   }
+  if (br_uses_s_key()) {
+    const size_t rows = (size_t)e->p.n * 2 * e->p.l;
+    if (!e->bsk3) CU(cudaMalloc(reinterpret_cast<void **>(&e->bsk3), rows * brs::kRowCplx * sizeof(cplx)));
+    CU(bsk_permute_s_launch(e->bsk(), e->bsk3, rows, e->stream));
+    e->launches++;
+  }
   if (ks_variant() == KS_UMMA && ks_umma_supported(e->p.basebit, e->p.iks_t)) {
     if (!e->kumma) CU(cudaMalloc(reinterpret_cast<void **>(&e->kumma), ks_umma_key_bytes(e->p.n, e->p.iks_t, e->p.basebit)));
     CU(ksk_umma_relayout_launch(e->ksk(), e->ksk_stride, e->kumma, e->p.n, e->p.iks_t, e->p.basebit, e->stream));
@@ -153,6 +179,32 @@ int ensure_blob(tfhe_engine *e) {
   blob_layout(e);
   CU(cudaMalloc(reinterpret_cast<void **>(&e->blob), e->blob_bytes));
   return TFHE_OK;
+}
+
+// LUT ids: decode to a slot, or -1 when the id is stale / unknown
+int lut_slot(const tfhe_engine *e, int lut_id) {
+  if (lut_id == 0) return 0;
+  if (lut_id < 0) return -1;
+  const int slot = lut_id & 0xff;
+  if ((uint32_t)(lut_id >> 8) != (e->key_epoch & 0x7fffffu)) return -1;
+  if (slot <= 0 || slot >= kScratchLut || !e->lut_used[slot]) return -1;
+  return slot;
+}
+int lut_make_id(const tfhe_engine *e, int slot) { return (int)((e->key_epoch & 0x7fffffu) << 8) | slot; }
+int lut_take_slot(tfhe_engine *e) {
+  for (int s = 1; s < kScratchLut; s++)
+    if (!e->lut_used[s]) { e->lut_used[s] = true; return s; }
+  return -1;
+}
+// a (re)loaded key invalidates every table id handed out before
+void lut_reset(tfhe_engine *e, int n_used = 1) {
+  for (int s = 0; s < kMaxLut; s++) e->lut_used[s] = s < n_used;
+  e->key_epoch++;
+}
+int lut_count(const tfhe_engine *e) {
+  int hi = 0;
+  for (int s = 0; s < kScratchLut; s++) if (e->lut_used[s]) hi = s + 1;
+  return hi;
 }
 
 // K4 dispatch: tensor-core GEMM for the gate sets, row-walk kernels otherwise
@@ -186,10 +238,11 @@ int run_device(tfhe_engine *e, tfhe_engine::Slot &sl, int op, const uint8_t *d_o
                const uint32_t *d_in, uint32_t *d_out, size_t count, int out_kind,
                const int32_t *d_lut_ids = nullptr) {
   if (!e->key_loaded) return fail(TFHE_ERR_NO_KEY, "cloud key not loaded");
-  if (lut_id >= e->n_lut) return fail(TFHE_ERR_INVALID, "unknown lut id %d", lut_id);
+  if (lut_id >= kMaxLut) return fail(TFHE_ERR_INVALID, "unknown lut slot %d", lut_id);
   BrArgs a{};
   a.bsk = e->bsk();
   a.bsk2 = e->bsk2;
+  a.bsk3 = e->bsk3; a.tw_s = e->tw_s;
   a.tw_a = e->tw_a; a.tw_b = e->tw_b;
   a.tv = e->tv(); a.tv_index = d_lut_ids; a.tv_default = lut_id < 0 ? 0 : lut_id;
   a.in = d_in; a.ops = d_ops; a.op = op;
@@ -229,6 +282,9 @@ int retire_slot(tfhe_engine::Slot &sl, float &ms0, float &ms1) {
 // Host-buffer driver: chunks of a few dozen persistent-grid rounds flow through a two-slot
 // pipeline (copy-in stream -> engine stream -> copy-out stream), so the host<->device copies of
 // neighbouring chunks overlap the kernels.
+int run_host_locked(tfhe_engine *e, int op, const uint8_t *ops, int lut_id, const uint32_t *in,
+                    size_t in_words, uint32_t *out, size_t out_words, size_t count, int out_kind,
+                    const int32_t *lut_ids = nullptr);
 int run_host(tfhe_engine *e, int op, const uint8_t *ops, int lut_id, const uint32_t *in,
              size_t in_words, uint32_t *out, size_t out_words, size_t count, int out_kind,
              const int32_t *lut_ids = nullptr) {
@@ -236,6 +292,13 @@ int run_host(tfhe_engine *e, int op, const uint8_t *ops, int lut_id, const uint3
   if (count == 0) return TFHE_OK;
   if (!in || !out) return fail(TFHE_ERR_INVALID, "null buffer");
   std::lock_guard<std::mutex> lock(e->mu);
+  return run_host_locked(e, op, ops, lut_id, in, in_words, out, out_words, count, out_kind, lut_ids);
+}
+int run_host_locked(tfhe_engine *e, int op, const uint8_t *ops, int lut_id, const uint32_t *in,
+                    size_t in_words, uint32_t *out, size_t out_words, size_t count, int out_kind,
+                    const int32_t *lut_ids) {
+  if (count == 0) return TFHE_OK;
+  if (!in || !out) return fail(TFHE_ERR_INVALID, "null buffer");
   CU(cudaSetDevice(e->dev));
   if (!e->key_loaded) return fail(TFHE_ERR_NO_KEY, "cloud key not loaded");
   float ms0 = 0.f, ms1 = 0.f;
@@ -295,6 +358,117 @@ int run_host(tfhe_engine *e, int op, const uint8_t *ops, int lut_id, const uint3
 
 }  // namespace
 
+// ---- NCCL, resolved at run time ----------------------------------------------------------------
+// The library does not link libnccl: a one-GPU caller needs none, and a host process that already
+// carries its own NCCL (e.g. PyTorch) must keep using that copy.  tfhe_engine_create_multi resolves
+// the five entry points it needs from the copy already in the process, else from libnccl.so.2.
+namespace {
+struct NcclApi {
+  ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+const NcclApi &nccl_api() {
+  static const NcclApi api = [] {
+    NcclApi a;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return a;
+    a.CommInitAll = reinterpret_cast<decltype(a.CommInitAll)>(dlsym(h, "ncclCommInitAll"));
+    a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    a.Broadcast = reinterpret_cast<decltype(a.Broadcast)>(dlsym(h, "ncclBroadcast"));
+    a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(dlsym(h, "ncclGroupStart"));
+    a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(dlsym(h, "ncclGroupEnd"));
+    a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    a.ok = a.CommInitAll && a.CommDestroy && a.Broadcast && a.GroupStart && a.GroupEnd && a.GetErrorString;
+    return a;
+  }();
+  return api;
+}
+#define NC(call)                                                                              \
+  do {                                                                                        \
+    ncclResult_t r_ = (call);                                                                 \
+    if (r_ != ncclSuccess)                                                                    \
+      return fail(TFHE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, nccl_api().GetErrorString(r_), \
+                  __FILE__, __LINE__);                                                        \
+  } while (0)
+
+// After the root engine's blob is final: one ncclBroadcast of the re-laid-out key (BSK | KSK | test
+// vectors) to every peer over NVLink, then each peer derives its kernel-specific key orders.
+int broadcast_key(tfhe_engine *e, int n_lut_used) {
+  if (e->peers.empty()) return TFHE_OK;
+  const NcclApi &nc = nccl_api();
+  ncclComm_t *comms = static_cast<ncclComm_t *>(e->nccl_comms);
+  for (tfhe_engine *p : e->peers) {
+    std::lock_guard<std::mutex> lock(p->mu);
+    CU(cudaSetDevice(p->dev));
+    int rc = ensure_blob(p);
+    if (rc != TFHE_OK) return rc;
+    if (p->blob_bytes != e->blob_bytes) return fail(TFHE_ERR_INVALID, "peer blob size differs");
+  }
+  CU(cudaSetDevice(e->dev));
+  CU(cudaStreamSynchronize(e->stream));
+  CU(cudaEventRecord(e->ev[0], e->stream));
+  NC(nc.GroupStart());
+  NC(nc.Broadcast(e->blob, e->blob, e->blob_bytes, ncclUint8, 0, comms[0], e->stream));
+  for (size_t i = 0; i < e->peers.size(); i++) {
+    tfhe_engine *p = e->peers[i];
+    NC(nc.Broadcast(p->blob, p->blob, p->blob_bytes, ncclUint8, 0, comms[i + 1], p->stream));
+  }
+  NC(nc.GroupEnd());
+  CU(cudaEventRecord(e->ev[1], e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  CU(cudaEventElapsedTime(&e->last_broadcast_ms, e->ev[0], e->ev[1]));
+  for (tfhe_engine *p : e->peers) {
+    std::lock_guard<std::mutex> lock(p->mu);
+    CU(cudaSetDevice(p->dev));
+    CU(cudaStreamSynchronize(p->stream));
+    p->decomp_offset = e->decomp_offset;
+    lut_reset(p, n_lut_used);
+    p->key_epoch = e->key_epoch;          // table ids are valid on every device
+    for (int sidx = 0; sidx < kMaxLut; sidx++) p->lut_used[sidx] = e->lut_used[sidx];
+    int rc = finalize_key(p);
+    if (rc != TFHE_OK) return rc;
+    p->key_loaded = true;
+  }
+  CU(cudaSetDevice(e->dev));
+  return TFHE_OK;
+}
+
+// Contiguous shards [r*count/G, (r+1)*count/G), one host thread per peer GPU; the root's
+// shard runs on the calling thread.  fn(engine, base, n) -> status.
+template <class F> int shard(tfhe_engine *e, size_t count, F fn) {
+  if (e->peers.empty()) return fn(e, (size_t)0, count);
+  const size_t G = e->peers.size() + 1;
+  std::vector<int> rcs(G, TFHE_OK);
+  std::vector<std::string> errs(G);
+  std::vector<std::thread> th;
+  auto range = [&](size_t r, size_t &b, size_t &n) { b = r * count / G; n = (r + 1) * count / G - b; };
+  for (size_t r = 1; r < G; r++)
+    th.emplace_back([&, r] {
+      size_t b, n;
+      range(r, b, n);
+      rcs[r] = fn(e->peers[r - 1], b, n);
+      if (rcs[r] != TFHE_OK) errs[r] = g_err;
+    });
+  size_t b0, n0;
+  range(0, b0, n0);
+  rcs[0] = fn(e, b0, n0);
+  for (auto &t : th) t.join();
+  float br = e->last_ms[0], ks = e->last_ms[1];
+  for (tfhe_engine *p : e->peers) { br = br > p->last_ms[0] ? br : p->last_ms[0]; ks = ks > p->last_ms[1] ? ks : p->last_ms[1]; }
+  e->last_ms[0] = br; e->last_ms[1] = ks;      // slowest device
+  for (size_t r = 1; r < G; r++)
+    if (rcs[r] != TFHE_OK) return fail(rcs[r], "device %d: %s", e->peers[r - 1]->dev, errs[r].c_str());
+  return rcs[0];
+}
+}  // namespace
+
 static int engine_init(tfhe_engine *e, int device_id) {
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device_id));
@@ -324,6 +498,16 @@ static int engine_init(tfhe_engine *e, int device_id) {
   CU(cudaMalloc(reinterpret_cast<void **>(&e->tw_b), tb.size() * sizeof(cplx)));
   CU(cudaMemcpy(e->tw_a, ta.data(), ta.size() * sizeof(cplx), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(e->tw_b, tb.data(), tb.size() * sizeof(cplx), cudaMemcpyHostToDevice));
+  {  // per-thread constants of the 128-thread kernel (brs_core.cuh)
+    std::vector<cplx> tws((size_t)brs::kT * brs::kTwPerThread);
+    for (int t = 0; t < brs::kT; t++) {
+      cplx tw[brs::kTwPerThread];
+      brs::make_tw(t, tw);
+      for (int k = 0; k < brs::kTwPerThread; k++) tws[(size_t)t * brs::kTwPerThread + k] = tw[k];
+    }
+    CU(cudaMalloc(reinterpret_cast<void **>(&e->tw_s), tws.size() * sizeof(cplx)));
+    CU(cudaMemcpy(e->tw_s, tws.data(), tws.size() * sizeof(cplx), cudaMemcpyHostToDevice));
+  }
   blob_layout(e);
   return TFHE_OK;
 }
@@ -377,12 +561,75 @@ int tfhe_engine_create(const tfhe_params *params, int device_id, tfhe_engine **o
   return TFHE_OK;
 }
 
+int tfhe_engine_create_multi(const tfhe_params *params, const int *device_ids, int n_devices,
+                             tfhe_engine **out) {
+  if (!params || !device_ids || !out) return fail(TFHE_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (n_devices < 1) return fail(TFHE_ERR_INVALID, "need at least one device");
+  for (int i = 0; i < n_devices; i++)
+    for (int j = 0; j < i; j++)
+      if (device_ids[i] == device_ids[j]) return fail(TFHE_ERR_INVALID, "device %d listed twice", device_ids[i]);
+  tfhe_engine *root = nullptr;
+  int rc = tfhe_engine_create(params, device_ids[0], &root);
+  if (rc != TFHE_OK) return rc;
+  if (n_devices == 1) { *out = root; return TFHE_OK; }
+  auto bail = [&](int code) {
+    char saved[sizeof(g_err)];
+    memcpy(saved, g_err, sizeof(saved));
+    tfhe_engine_destroy(root);
+    memcpy(g_err, saved, sizeof(saved));
+    return code;
+  };
+  if (!nccl_api().ok) {
+    fail(TFHE_ERR_CUDA, "NCCL not found (libnccl.so.2): needed for the multi-GPU cloud-key broadcast");
+    return bail(TFHE_ERR_CUDA);
+  }
+  for (int i = 1; i < n_devices; i++) {
+    tfhe_engine *p = nullptr;
+    rc = tfhe_engine_create(params, device_ids[i], &p);
+    if (rc != TFHE_OK) return bail(rc);
+    root->peers.push_back(p);
+  }
+  ncclComm_t *comms = new (std::nothrow) ncclComm_t[n_devices]();
+  if (!comms) { fail(TFHE_ERR_ALLOC, "out of host memory"); return bail(TFHE_ERR_ALLOC); }
+  root->nccl_comms = comms;
+  ncclResult_t nr = nccl_api().CommInitAll(comms, n_devices, device_ids);
+  if (nr != ncclSuccess) {
+    fail(TFHE_ERR_CUDA, "ncclCommInitAll failed: %s", nccl_api().GetErrorString(nr));
+    delete[] comms;
+    root->nccl_comms = nullptr;
+    return bail(TFHE_ERR_CUDA);
+  }
+  cudaSetDevice(device_ids[0]);
+  *out = root;
+  return TFHE_OK;
+}
+
+int tfhe_engine_device_count(const tfhe_engine *e) { return e ? (int)e->peers.size() + 1 : 0; }
+
+int tfhe_engine_last_broadcast_ms(tfhe_engine *e, float *ms_out) {
+  if (!e || !ms_out) return fail(TFHE_ERR_INVALID, "null argument");
+  *ms_out = e->last_broadcast_ms;
+  return TFHE_OK;
+}
+
 void tfhe_engine_destroy(tfhe_engine *e) {
   if (!e) return;
+  if (e->nccl_comms) {
+    ncclComm_t *comms = static_cast<ncclComm_t *>(e->nccl_comms);
+    for (size_t i = 0; i < e->peers.size() + 1; i++)
+      if (comms[i]) nccl_api().CommDestroy(comms[i]);
+    delete[] comms;
+    e->nccl_comms = nullptr;
+  }
+  for (tfhe_engine *p : e->peers) tfhe_engine_destroy(p);
+  e->peers.clear();
   cudaSetDevice(e->dev);
   cudaDeviceSynchronize();
   if (e->blob) cudaFree(e->blob);
   if (e->bsk2) cudaFree(e->bsk2);
+  if (e->bsk3) cudaFree(e->bsk3);
+  if (e->tw_s) cudaFree(e->tw_s);
   if (e->kumma) cudaFree(e->kumma);
   if (e->kmma) cudaFree(e->kmma);
   if (e->tw_a) cudaFree(e->tw_a);
@@ -407,7 +654,12 @@ int tfhe_engine_set_stream(tfhe_engine *e, void *cuda_stream) {
   return TFHE_OK;
 }
 
-uint64_t tfhe_engine_kernel_launches(const tfhe_engine *e) { return e ? e->launches : 0; }
+uint64_t tfhe_engine_kernel_launches(const tfhe_engine *e) {
+  if (!e) return 0;
+  uint64_t n = e->launches;
+  for (const tfhe_engine *p : e->peers) n += p->launches;
+  return n;
+}
 
 int tfhe_engine_last_kernel_ms(tfhe_engine *e, float out_ms[2]) {
   if (!e || !out_ms) return fail(TFHE_ERR_INVALID, "null argument");
@@ -465,15 +717,32 @@ int tfhe_engine_load_cloud_key(tfhe_engine *e, uint32_t decomposition_offset,
   CU(cudaStreamSynchronize(e->stream));
   e->s_misc.release();
   e->decomp_offset = decomposition_offset;
-  e->n_lut = 1;
+  lut_reset(e);
   { int rc_ = finalize_key(e); if (rc_ != TFHE_OK) return rc_; }
   e->key_loaded = true;
-  return TFHE_OK;
+  return broadcast_key(e, 1);
 }
 
 int tfhe_engine_generate_cloud_key(tfhe_engine *e, const uint32_t *s0, const uint32_t *s1,
                                    double alpha_lv0, double alpha_lv1, uint64_t seed) {
   if (!e || !s0 || !s1) return fail(TFHE_ERR_INVALID, "null argument");
+  // 256-bit generator key: OS entropy (seed == 0, the secure default -- the reference draws from
+  // rand::thread_rng, an OS-seeded ChaCha generator), or expanded from `seed` for reproducible
+  // TESTS ONLY (a 64-bit seed caps the key's security at 2^64 at best).
+  uint32_t key256[8];
+  if (seed == 0) {
+    if (getentropy(key256, sizeof(key256)) != 0) return fail(TFHE_ERR_INVALID, "getentropy failed");
+  } else {
+    uint64_t z = seed;
+    for (int i = 0; i < 4; i++) {   // SplitMix64
+      z += 0x9E3779B97F4A7C15ull;
+      uint64_t x = z;
+      x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+      x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+      x ^= x >> 31;
+      key256[2 * i] = (uint32_t)x; key256[2 * i + 1] = (uint32_t)(x >> 32);
+    }
+  }
   std::lock_guard<std::mutex> lock(e->mu);
   CU(cudaSetDevice(e->dev));
   int rc = ensure_blob(e);
@@ -492,7 +761,7 @@ int tfhe_engine_generate_cloud_key(tfhe_engine *e, const uint32_t *s0, const uin
   CU(keygen_launch(e->tw_a, e->tw_b, reinterpret_cast<const uint32_t *>(sc),
                    reinterpret_cast<const uint32_t *>(sc + off_s1),
                    reinterpret_cast<cplx *>(sc + off_spec), reinterpret_cast<cplx *>(e->blob),
-                   d_ksk_ref, p.n, p.l, p.bgbit, p.basebit, p.iks_t, alpha_lv0, alpha_lv1, seed,
+                   d_ksk_ref, p.n, p.l, p.bgbit, p.basebit, p.iks_t, alpha_lv0, alpha_lv1, key256,
                    e->stream));
   CU(ksk_relayout_launch(d_ksk_ref, reinterpret_cast<uint32_t *>(e->blob + e->off_ksk), e->ksk_rows,
                          p.n, e->ksk_stride, e->stream));
@@ -507,10 +776,10 @@ int tfhe_engine_generate_cloud_key(tfhe_engine *e, const uint32_t *s0, const uin
   uint32_t offset = 0;
   for (uint32_t i = 0; i < p.l; i++) offset += (1u << (p.bgbit - 1)) << (32 - (i + 1) * p.bgbit);
   e->decomp_offset = offset;
-  e->n_lut = 1;
+  lut_reset(e);
   { int rc_ = finalize_key(e); if (rc_ != TFHE_OK) return rc_; }
   e->key_loaded = true;
-  return TFHE_OK;
+  return broadcast_key(e, 1);
 }
 
 int tfhe_engine_alloc_cloud_key(tfhe_engine *e) {
@@ -530,10 +799,11 @@ int tfhe_engine_cloud_key_blob(tfhe_engine *e, void **device_ptr, size_t *bytes)
 
 int tfhe_engine_commit_cloud_key(tfhe_engine *e, uint32_t decomposition_offset) {
   if (!e) return fail(TFHE_ERR_INVALID, "null engine");
-  if (!e->blob) return fail(TFHE_ERR_NO_KEY, "cloud key blob not allocated");
   std::lock_guard<std::mutex> lock(e->mu);
+  if (!e->blob) return fail(TFHE_ERR_NO_KEY, "cloud key blob not allocated");
+  CU(cudaSetDevice(e->dev));   // several engines may live in one process: the re-layout kernels go to OUR device
   e->decomp_offset = decomposition_offset;
-  e->n_lut = 1;
+  lut_reset(e);
   { int rc_ = finalize_key(e); if (rc_ != TFHE_OK) return rc_; }
   e->key_loaded = true;
   return TFHE_OK;
@@ -566,7 +836,7 @@ int tfhe_engine_export_cloud_key(tfhe_engine *e, void *host_buf, size_t bytes) {
   memcpy(hd.magic, "TFHEB200", 8);
   hd.version = kBlobFormat;
   hd.n = e->p.n; hd.N = e->p.N; hd.l = e->p.l; hd.bgbit = e->p.bgbit; hd.basebit = e->p.basebit;
-  hd.iks_t = e->p.iks_t; hd.decomposition_offset = e->decomp_offset; hd.n_lut = (uint32_t)e->n_lut;
+  hd.iks_t = e->p.iks_t; hd.decomposition_offset = e->decomp_offset; hd.n_lut = (uint32_t)lut_count(e);
   hd.payload_bytes = e->blob_bytes;
   memcpy(host_buf, &hd, sizeof(hd));
   CU(cudaMemcpyAsync(static_cast<uint8_t *>(host_buf) + sizeof(hd), e->blob, e->blob_bytes,
@@ -592,15 +862,15 @@ int tfhe_engine_import_cloud_key(tfhe_engine *e, const void *host_buf, size_t by
   if (rc != TFHE_OK) return rc;
   if (hd.payload_bytes != e->blob_bytes || bytes < sizeof(hd) + hd.payload_bytes)
     return fail(TFHE_ERR_INVALID, "blob size mismatch");
-  if (hd.n_lut < 1 || hd.n_lut > (uint32_t)kMaxLut) return fail(TFHE_ERR_INVALID, "bad lut count");
+  if (hd.n_lut < 1 || hd.n_lut > (uint32_t)kScratchLut) return fail(TFHE_ERR_INVALID, "bad lut count");
   CU(cudaMemcpyAsync(e->blob, static_cast<const uint8_t *>(host_buf) + sizeof(hd), e->blob_bytes,
                      cudaMemcpyHostToDevice, e->stream));
   CU(cudaStreamSynchronize(e->stream));
   e->decomp_offset = hd.decomposition_offset;
-  e->n_lut = (int)hd.n_lut;
+  lut_reset(e, (int)hd.n_lut);   // slots 1..n_lut-1 of the blob stay addressable under the new epoch
   { int rc_ = finalize_key(e); if (rc_ != TFHE_OK) return rc_; }
   e->key_loaded = true;
-  return TFHE_OK;
+  return broadcast_key(e, (int)hd.n_lut);
 }
 
 int tfhe_batch_gate(tfhe_engine *e, tfhe_gate op, const uint32_t *in_pairs, uint32_t *out,
@@ -608,7 +878,9 @@ int tfhe_batch_gate(tfhe_engine *e, tfhe_gate op, const uint32_t *in_pairs, uint
   if (!e) return fail(TFHE_ERR_INVALID, "null engine");
   if ((int)op < 0 || (int)op >= TFHE_GATE_COUNT) return fail(TFHE_ERR_INVALID, "bad gate %d", (int)op);
   const size_t w = e->p.n + 1;
-  return run_host(e, (int)op, nullptr, -1, in_pairs, 2 * w, out, w, count, 0);
+  return shard(e, count, [&](tfhe_engine *d, size_t b, size_t n) {
+    return run_host(d, (int)op, nullptr, -1, in_pairs + b * 2 * w, 2 * w, out + b * w, w, n, 0);
+  });
 }
 
 int tfhe_batch_gate_mixed(tfhe_engine *e, const uint8_t *ops, const uint32_t *in_pairs,
@@ -618,34 +890,99 @@ int tfhe_batch_gate_mixed(tfhe_engine *e, const uint8_t *ops, const uint32_t *in
   for (size_t i = 0; i < count; i++)
     if (ops[i] >= TFHE_GATE_COUNT) return fail(TFHE_ERR_INVALID, "bad gate %d at %zu", ops[i], i);
   const size_t w = e->p.n + 1;
-  return run_host(e, 0, ops, -1, in_pairs, 2 * w, out, w, count, 0);
+  return shard(e, count, [&](tfhe_engine *d, size_t b, size_t n) {
+    return run_host(d, 0, ops + b, -1, in_pairs + b * 2 * w, 2 * w, out + b * w, w, n, 0);
+  });
 }
 
 int tfhe_batch_bootstrap(tfhe_engine *e, const uint32_t *in, uint32_t *out, size_t count,
                          int key_switch) {
   if (!e) return fail(TFHE_ERR_INVALID, "null engine");
   const size_t w = e->p.n + 1;
-  return run_host(e, -1, nullptr, -1, in, w, out, w, count, key_switch ? 0 : 1);
+  return shard(e, count, [&](tfhe_engine *d, size_t b, size_t n) {
+    return run_host(d, -1, nullptr, -1, in + b * w, w, out + b * w, w, n, key_switch ? 0 : 1);
+  });
 }
 
 int tfhe_batch_blind_rotate(tfhe_engine *e, const uint32_t *in, uint32_t *out_trlwe, size_t count) {
   if (!e) return fail(TFHE_ERR_INVALID, "null engine");
-  return run_host(e, -1, nullptr, -1, in, e->p.n + 1, out_trlwe, 2 * TFHE_N, count, 2);
+  const size_t w = e->p.n + 1;
+  return shard(e, count, [&](tfhe_engine *d, size_t b, size_t n) {
+    return run_host(d, -1, nullptr, -1, in + b * w, w, out_trlwe + b * 2 * TFHE_N, 2 * TFHE_N, n, 2);
+  });
 }
 
-int tfhe_lut_register(tfhe_engine *e, const uint32_t *poly_a, const uint32_t *poly_b,
-                      int *lut_id_out) {
-  if (!e || !poly_b || !lut_id_out) return fail(TFHE_ERR_INVALID, "null argument");
-  std::lock_guard<std::mutex> lock(e->mu);
-  if (!e->blob) return fail(TFHE_ERR_NO_KEY, "cloud key not loaded");
-  if (e->n_lut >= kMaxLut) return fail(TFHE_ERR_ALLOC, "out of LUT slots (%d)", kMaxLut);
+// lut/generator.rs:89-137 on the device into test-vector slot `sidx` (engine lock held)
+static int generate_into_slot(tfhe_engine *e, int sidx, const uint32_t *f_table, uint32_t modulus,
+                              double scale, uint32_t *lut_b_out) {
+  if (scale <= 0.0) scale = 1.0 / (2.0 * (double)modulus);  // lut/encoder.rs:36
+  CU(e->s_misc.reserve((size_t)modulus * 4));
+  CU(cudaMemcpyAsync(e->s_misc.p, f_table, (size_t)modulus * 4, cudaMemcpyHostToDevice, e->stream));
+  uint32_t *slot = e->tv() + (size_t)sidx * 2 * TFHE_N;
+  CU(lut_generate_launch(static_cast<const uint32_t *>(e->s_misc.p), modulus, scale, slot, e->stream));
+  e->launches++;
+  if (lut_b_out)
+    CU(cudaMemcpyAsync(lut_b_out, slot + TFHE_N, TFHE_N * 4, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return TFHE_OK;
+}
+
+// fill test-vector slot `sidx` of ONE device with a caller-made polynomial pair (engine lock held)
+static int register_into_slot(tfhe_engine *e, int sidx, const uint32_t *poly_a, const uint32_t *poly_b) {
   CU(cudaSetDevice(e->dev));
-  uint32_t *slot = e->tv() + (size_t)e->n_lut * 2 * TFHE_N;
+  uint32_t *slot = e->tv() + (size_t)sidx * 2 * TFHE_N;
   if (poly_a) CU(cudaMemcpyAsync(slot, poly_a, TFHE_N * 4, cudaMemcpyHostToDevice, e->stream));
   else CU(cudaMemsetAsync(slot, 0, TFHE_N * 4, e->stream));
   CU(cudaMemcpyAsync(slot + TFHE_N, poly_b, TFHE_N * 4, cudaMemcpyHostToDevice, e->stream));
   CU(cudaStreamSynchronize(e->stream));
-  *lut_id_out = e->n_lut++;
+  return TFHE_OK;
+}
+// Tables live in the same slot on every device of a multi-GPU engine: the root picks the slot, the
+// peers mirror it.  fill(engine) writes the slot on one device.
+extern "C++" {
+template <class F> static int lut_new(tfhe_engine *e, F fill, int *lut_id_out) {
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (!e->blob) return fail(TFHE_ERR_NO_KEY, "cloud key not loaded");
+  const int sidx = lut_take_slot(e);
+  if (sidx < 0)
+    return fail(TFHE_ERR_ALLOC, "out of LUT slots (%d); release tables with tfhe_lut_release", kScratchLut - 1);
+  int rc = fill(e, sidx, true);
+  for (size_t i = 0; rc == TFHE_OK && i < e->peers.size(); i++) {
+    tfhe_engine *p = e->peers[i];
+    std::lock_guard<std::mutex> plock(p->mu);
+    rc = fill(p, sidx, false);
+    if (rc == TFHE_OK) p->lut_used[sidx] = true;
+  }
+  if (rc != TFHE_OK) {
+    e->lut_used[sidx] = false;
+    for (tfhe_engine *p : e->peers) p->lut_used[sidx] = false;
+    return rc;
+  }
+  CU(cudaSetDevice(e->dev));
+  *lut_id_out = lut_make_id(e, sidx);
+  return TFHE_OK;
+}
+}  // extern "C++"
+
+int tfhe_lut_register(tfhe_engine *e, const uint32_t *poly_a, const uint32_t *poly_b,
+                      int *lut_id_out) {
+  if (!e || !poly_b || !lut_id_out) return fail(TFHE_ERR_INVALID, "null argument");
+  return lut_new(e, [&](tfhe_engine *d, int sidx, bool) { return register_into_slot(d, sidx, poly_a, poly_b); },
+                 lut_id_out);
+}
+
+int tfhe_lut_release(tfhe_engine *e, int lut_id) {
+  if (!e) return fail(TFHE_ERR_INVALID, "null engine");
+  std::lock_guard<std::mutex> lock(e->mu);
+  const int sidx = lut_slot(e, lut_id);
+  if (sidx <= 0) return fail(TFHE_ERR_INVALID, "unknown or stale lut id %d", lut_id);
+  CU(cudaSetDevice(e->dev));
+  CU(cudaStreamSynchronize(e->stream));   // no queued kernel still reads the slot
+  e->lut_used[sidx] = false;
+  for (tfhe_engine *p : e->peers) {
+    std::lock_guard<std::mutex> plock(p->mu);
+    p->lut_used[sidx] = false;
+  }
   return TFHE_OK;
 }
 
@@ -653,40 +990,110 @@ int tfhe_lut_generate(tfhe_engine *e, const uint32_t *f_table, uint32_t modulus,
                       uint32_t *lut_b_out, int *lut_id_out) {
   if (!e || !f_table || !lut_id_out) return fail(TFHE_ERR_INVALID, "null argument");
   if (modulus == 0 || modulus > TFHE_N) return fail(TFHE_ERR_INVALID, "bad modulus %u", modulus);
-  std::lock_guard<std::mutex> lock(e->mu);
-  if (!e->blob) return fail(TFHE_ERR_NO_KEY, "cloud key not loaded");
-  if (e->n_lut >= kMaxLut) return fail(TFHE_ERR_ALLOC, "out of LUT slots (%d)", kMaxLut);
-  CU(cudaSetDevice(e->dev));
-  if (scale <= 0.0) scale = 1.0 / (2.0 * (double)modulus);  // lut/encoder.rs:36
-  CU(e->s_misc.reserve((size_t)modulus * 4));
-  CU(cudaMemcpyAsync(e->s_misc.p, f_table, (size_t)modulus * 4, cudaMemcpyHostToDevice, e->stream));
-  uint32_t *slot = e->tv() + (size_t)e->n_lut * 2 * TFHE_N;
-  CU(lut_generate_launch(static_cast<const uint32_t *>(e->s_misc.p), modulus, scale, slot, e->stream));
-  e->launches++;
-  if (lut_b_out)
-    CU(cudaMemcpyAsync(lut_b_out, slot + TFHE_N, TFHE_N * 4, cudaMemcpyDeviceToHost, e->stream));
-  CU(cudaStreamSynchronize(e->stream));
-  *lut_id_out = e->n_lut++;
-  return TFHE_OK;
+  return lut_new(e, [&](tfhe_engine *d, int sidx, bool root) -> int {
+    CU(cudaSetDevice(d->dev));
+    return generate_into_slot(d, sidx, f_table, modulus, scale, root ? lut_b_out : nullptr);
+  }, lut_id_out);
+}
+
+int tfhe_batch_bootstrap_func(tfhe_engine *e, const uint32_t *f_table, uint32_t modulus, double scale,
+                              const uint32_t *in, uint32_t *out, size_t count) {
+  if (!e || !f_table) return fail(TFHE_ERR_INVALID, "null argument");
+  if (modulus == 0 || modulus > TFHE_N) return fail(TFHE_ERR_INVALID, "bad modulus %u", modulus);
+  const size_t w = e->p.n + 1;
+  return shard(e, count, [&](tfhe_engine *d, size_t b, size_t n) -> int {
+    std::lock_guard<std::mutex> lock(d->mu);   // table generation and its use are one critical section
+    if (!d->key_loaded) return fail(TFHE_ERR_NO_KEY, "cloud key not loaded");
+    CU(cudaSetDevice(d->dev));
+    // the previous call's kernels have finished (run_host synchronises), so the scratch slot is free
+    const int rc = generate_into_slot(d, kScratchLut, f_table, modulus, scale, nullptr);
+    if (rc != TFHE_OK) return rc;
+    return run_host_locked(d, -1, nullptr, kScratchLut, in + b * w, w, out + b * w, w, n, 0);
+  });
 }
 
 int tfhe_batch_bootstrap_lut(tfhe_engine *e, int lut_id, const uint32_t *in, uint32_t *out,
                              size_t count) {
   if (!e) return fail(TFHE_ERR_INVALID, "null engine");
-  if (lut_id < 0 || lut_id >= e->n_lut) return fail(TFHE_ERR_INVALID, "unknown lut id %d", lut_id);
+  int sidx;
+  {
+    std::lock_guard<std::mutex> lock(e->mu);
+    sidx = lut_slot(e, lut_id);
+  }
+  if (sidx < 0) return fail(TFHE_ERR_INVALID, "unknown or stale lut id %d", lut_id);
   const size_t w = e->p.n + 1;
-  return run_host(e, -1, nullptr, lut_id, in, w, out, w, count, 0);
+  return shard(e, count, [&](tfhe_engine *d, size_t b, size_t n) {
+    return run_host(d, -1, nullptr, sidx, in + b * w, w, out + b * w, w, n, 0);
+  });
 }
 
 int tfhe_batch_bootstrap_lut_multi(tfhe_engine *e, const int32_t *lut_ids, const uint32_t *in,
                                    uint32_t *out, size_t count) {
   if (!e) return fail(TFHE_ERR_INVALID, "null engine");
   if (!lut_ids && count) return fail(TFHE_ERR_INVALID, "null lut_ids");
-  for (size_t i = 0; i < count; i++)
-    if (lut_ids[i] < 0 || lut_ids[i] >= e->n_lut)
-      return fail(TFHE_ERR_INVALID, "unknown lut id %d at %zu", lut_ids[i], i);
+  std::vector<int32_t> slots;
+  try { slots.resize(count); } catch (...) { return fail(TFHE_ERR_ALLOC, "out of host memory"); }
+  {
+    std::lock_guard<std::mutex> lock(e->mu);
+    for (size_t i = 0; i < count; i++) {
+      const int sidx = lut_slot(e, lut_ids[i]);
+      if (sidx < 0) return fail(TFHE_ERR_INVALID, "unknown or stale lut id %d at %zu", lut_ids[i], i);
+      slots[i] = sidx;
+    }
+  }
   const size_t w = e->p.n + 1;
-  return run_host(e, -1, nullptr, 0, in, w, out, w, count, 0, lut_ids);
+  return shard(e, count, [&](tfhe_engine *d, size_t b, size_t n) {
+    return run_host(d, -1, nullptr, 0, in + b * w, w, out + b * w, w, n, 0, slots.data() + b);
+  });
+}
+
+// ---- FFTProcessor seam (fft/mod.rs:80-107) ------------------------------------------------------
+static int run_seam(tfhe_engine *e, int mode, const void *in_a, const uint32_t *in_b, void *out,
+                    size_t count) {
+  if (!e) return fail(TFHE_ERR_INVALID, "null engine");
+  if (count == 0) return TFHE_OK;
+  if (!in_a || !out || (mode == MODE_POLYMUL && !in_b)) return fail(TFHE_ERR_INVALID, "null buffer");
+  std::lock_guard<std::mutex> lock(e->mu);
+  CU(cudaSetDevice(e->dev));
+  const size_t in_bytes = (size_t)TFHE_N * (mode == MODE_FFT ? 8 : 4);
+  const size_t out_bytes = (size_t)TFHE_N * (mode == MODE_IFFT ? 8 : 4);
+  const size_t chunk = 1u << 15;
+  float ms_total = 0.f;
+  tfhe_engine::Slot &sl = e->slot[0];
+  for (size_t base = 0; base < count; base += chunk) {
+    const size_t c = count - base < chunk ? count - base : chunk;
+    CU(sl.in.reserve(c * in_bytes));
+    CU(sl.out.reserve(c * out_bytes));
+    CU(cudaMemcpyAsync(sl.in.p, static_cast<const uint8_t *>(in_a) + base * in_bytes, c * in_bytes,
+                       cudaMemcpyHostToDevice, e->stream));
+    const uint32_t *d_b = nullptr;
+    if (mode == MODE_POLYMUL) {
+      CU(sl.ext.reserve(c * in_bytes));
+      CU(cudaMemcpyAsync(sl.ext.p, in_b + base * TFHE_N, c * in_bytes, cudaMemcpyHostToDevice, e->stream));
+      d_b = static_cast<const uint32_t *>(sl.ext.p);
+    }
+    CU(cudaEventRecord(sl.br_start, e->stream));
+    CU(fft_seam_launch(mode, e->tw_s, sl.in.p, d_b, sl.out.p, c, e->num_sms, e->stream));
+    e->launches++;
+    CU(cudaEventRecord(sl.br_end, e->stream));
+    CU(cudaMemcpyAsync(static_cast<uint8_t *>(out) + base * out_bytes, sl.out.p, c * out_bytes,
+                       cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, sl.br_start, sl.br_end));
+    ms_total += ms;
+  }
+  e->last_ms[0] = ms_total; e->last_ms[1] = 0.f;
+  return TFHE_OK;
+}
+int tfhe_batch_ifft(tfhe_engine *e, const uint32_t *in, double *out, size_t count) {
+  return run_seam(e, MODE_IFFT, in, nullptr, out, count);
+}
+int tfhe_batch_fft(tfhe_engine *e, const double *in, uint32_t *out, size_t count) {
+  return run_seam(e, MODE_FFT, in, nullptr, out, count);
+}
+int tfhe_batch_poly_mul(tfhe_engine *e, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t count) {
+  return run_seam(e, MODE_POLYMUL, a, b, out, count);
 }
 
 int tfhe_batch_extract_key_switch(tfhe_engine *e, const uint32_t *in_trlwe, uint32_t *out,
@@ -813,6 +1220,10 @@ int tfhe_batch_bootstrap_dev(tfhe_engine *e, int lut_id, const uint32_t *d_in, u
   if (count == 0) return TFHE_OK;
   std::lock_guard<std::mutex> lock(e->mu);
   CU(cudaSetDevice(e->dev));
+  if (lut_id >= 0) {
+    lut_id = lut_slot(e, lut_id);
+    if (lut_id < 0) return fail(TFHE_ERR_INVALID, "unknown or stale lut id");
+  }
   const size_t w = e->p.n + 1;
   for (size_t base = 0; base < count; base += kChunk) {
     size_t c = count - base < kChunk ? count - base : kChunk;

@@ -13,6 +13,8 @@ enum { BR_OUT_TRLWE = 0, BR_OUT_EXTRACT = 1, BR_OUT_EXTRACT2 = 2 };
 struct BrArgs {
   const cplx *bsk;          // device order: cplx[n][2l][8][2][64] (br_core.cuh)
   const cplx *bsk2;         // same rows, thread slots permuted for the TMEM-exchange kernel (or NULL)
+  const cplx *bsk3;         // same rows in the 128-thread kernel's order [kd][o][T] (brs_core.cuh), or NULL
+  const cplx *tw_s;         // [128][20] per-thread constants of the 128-thread kernel
   const cplx *tw_a;         // [64][8]
   const cplx *tw_b;         // [8][8]
   const uint32_t *tv;       // test vectors u32[slot][2][N]; slot 0 = cloud-key test vector
@@ -26,11 +28,21 @@ struct BrArgs {
   uint32_t n;
   uint32_t offset;          // CloudKey.decomposition_offset, used verbatim
   size_t count;
+  uint32_t stagger;         // 128-thread kernel: start offset between the CTA's ciphertext groups, in cycles
 };
 bool br_supported(uint32_t l, uint32_t bgbit);
 bool br_uses_permuted_key();  // the selected throughput kernel reads BrArgs::bsk2
+bool br_uses_s_key();         // the selected throughput kernel reads BrArgs::bsk3 / tw_s
 cudaError_t br_launch(uint32_t l, uint32_t bgbit, const BrArgs &args, int num_sms,
                       cudaStream_t stream);
+// 128-thread-per-ciphertext throughput kernel (blind_rotate_s.cu)
+cudaError_t br_launch_s(uint32_t l, uint32_t bgbit, const BrArgs &args, int num_sms,
+                        cudaStream_t stream);
+
+// FFTProcessor seam (fft_seam.cu): standalone batch transforms on the blind rotation's passes
+enum { MODE_IFFT = 0, MODE_FFT = 1, MODE_POLYMUL = 2 };
+cudaError_t fft_seam_launch(int mode, const cplx *tw_s, const void *in_a, const uint32_t *in_b, void *out,
+                            size_t count, int num_sms, cudaStream_t stream);
 
 // K4 (keyswitch.cu)
 struct KsArgs {
@@ -78,6 +90,7 @@ cudaError_t ksk_umma_relayout_launch(const uint32_t *blob_rows, uint32_t stride,
 cudaError_t bsk_relayout_launch(const double *src_ref, cplx *dst, uint32_t n, uint32_t l2,
                                 cudaStream_t stream);
 cudaError_t bsk_permute_launch(const cplx *src, cplx *dst, size_t rows, cudaStream_t stream);
+cudaError_t bsk_permute_s_launch(const cplx *src, cplx *dst, size_t rows, cudaStream_t stream);
 cudaError_t ksk_relayout_launch(const uint32_t *src_ref, uint32_t *dst, uint32_t rows, uint32_t n,
                                 uint32_t stride, cudaStream_t stream);
 cudaError_t lut_generate_launch(const uint32_t *d_f_table, uint32_t modulus, double scale,
@@ -90,4 +103,4 @@ cudaError_t fp64_probe_launch(double *d_sink, int blocks, int iters, cudaStream_
 cudaError_t keygen_launch(const cplx *tw_a, const cplx *tw_b, const uint32_t *d_s0,
                           const uint32_t *d_s1, cplx *d_s1_spec, cplx *d_bsk, uint32_t *d_ksk_ref,
                           uint32_t n, uint32_t l, uint32_t bgbit, uint32_t basebit, uint32_t t,
-                          double alpha_lv0, double alpha_lv1, uint64_t seed, cudaStream_t stream);
+                          double alpha_lv0, double alpha_lv1, const uint32_t key256[8], cudaStream_t stream);

@@ -5,7 +5,8 @@
 // src/trlwe.rs:30-52, plus mu*Bg^-(r+1) on a[0] / b[0]) followed by the Fourier conversion
 // (src/trgsw.rs:58-68, src/trlwe.rs:91-96); and key::gen_key_switching_key (src/key.rs:102-122).
 // The reference draws from an unseeded thread_rng, so there is nothing to match bit for bit:
-// the generator here is counter-based Philox4x32-10 keyed by the caller's seed, and the tests
+// the generator here is the ChaCha20 block function used counter-based under a 256-bit key (OS
+// entropy unless the caller asks for a reproducible test key), and the tests
 // check the *structure* (b - a*s1 = noise + message with the right noise level) exactly.
 //
 // One CTA of 64 threads produces one TRGSW row: it draws a, forms a*s1 with the same
@@ -18,18 +19,31 @@ using namespace br;
 
 namespace {
 
-// ---- Philox4x32-10 (Salmon et al.), counter-based: one call = 4 x u32 ----------------------
-__device__ __forceinline__ uint4 philox(uint4 ctr, uint2 key) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+// ---- ChaCha20 block function (RFC 8439) as a counter-based generator: one call = 4 x u32 --------
+// The a-words of every key row are published verbatim, so the generator must be a CSPRNG: with a
+// non-cryptographic generator, recovering its state from the masks would reveal every noise term and
+// with it the secret keys.  key = 256 bits (OS entropy by default, engine.cu), block counter and
+// nonce = the caller's (row, index, stream tag) tuple; the first four words of the block are used.
+struct ChaChaKey { uint32_t k[8]; };
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, int n) { return (x << n) | (x >> (32 - n)); }
+#define CHACHA_QR(a, b, c, d)          \
+  a += b; d ^= a; d = rotl32(d, 16);   \
+  c += d; b ^= c; b = rotl32(b, 12);   \
+  a += b; d ^= a; d = rotl32(d, 8);    \
+  c += d; b ^= c; b = rotl32(b, 7);
+__device__ __forceinline__ uint4 philox(uint4 ctr, const ChaChaKey &key) {   // (name kept: call sites)
+  uint32_t x0 = 0x61707865u, x1 = 0x3320646eu, x2 = 0x79622d32u, x3 = 0x6b206574u;
+  uint32_t x4 = key.k[0], x5 = key.k[1], x6 = key.k[2], x7 = key.k[3];
+  uint32_t x8 = key.k[4], x9 = key.k[5], x10 = key.k[6], x11 = key.k[7];
+  uint32_t x12 = ctr.x, x13 = ctr.y, x14 = ctr.z, x15 = ctr.w;
 #pragma unroll
-  for (int r = 0; r < 10; r++) {
-    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += W0; key.y += W1;
+  for (int r = 0; r < 10; r++) {   // 20 rounds = 10 double rounds
+    CHACHA_QR(x0, x4, x8, x12) CHACHA_QR(x1, x5, x9, x13) CHACHA_QR(x2, x6, x10, x14) CHACHA_QR(x3, x7, x11, x15)
+    CHACHA_QR(x0, x5, x10, x15) CHACHA_QR(x1, x6, x11, x12) CHACHA_QR(x2, x7, x8, x13) CHACHA_QR(x3, x4, x9, x14)
   }
-  return ctr;
+  return make_uint4(x0 + 0x61707865u, x1 + 0x3320646eu, x2 + 0x79622d32u, x3 + 0x6b206574u);
 }
+#undef CHACHA_QR
 // utils.rs:9-12
 __device__ __forceinline__ uint32_t f64_to_torus_dev(double d) {
   return (uint32_t)(unsigned long long)(long long)(fmod(d, 1.0) * 4294967296.0);
@@ -49,7 +63,7 @@ struct KgArgs {
   cplx *bsk;                 // device BSK layout
   uint32_t n, l, bgbit;
   double alpha;
-  uint2 seed;
+  ChaChaKey seed;
 };
 
 __device__ __forceinline__ void load_tw(const KgArgs &a, int tid, cplx (&ta)[8], cplx (&tb)[8]) {
@@ -154,7 +168,7 @@ __global__ void __launch_bounds__(64) kg_bsk_row_kernel(const KgArgs a) {
 // key.rs:102-122 in the reference row layout u32[N*t*base][n+1]; one warp per row, k = 0 rows zero
 __global__ void kg_ksk_kernel(const uint32_t *__restrict__ s0, const uint32_t *__restrict__ s1,
                               uint32_t *__restrict__ ksk, uint32_t n, uint32_t basebit, uint32_t t,
-                              double alpha, uint2 seed) {
+                              double alpha, ChaChaKey seed) {
   const uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t base = 1u << basebit;
@@ -190,15 +204,16 @@ __global__ void kg_ksk_kernel(const uint32_t *__restrict__ s0, const uint32_t *_
 cudaError_t keygen_launch(const cplx *tw_a, const cplx *tw_b, const uint32_t *d_s0,
                           const uint32_t *d_s1, cplx *d_s1_spec, cplx *d_bsk, uint32_t *d_ksk_ref,
                           uint32_t n, uint32_t l, uint32_t bgbit, uint32_t basebit, uint32_t t,
-                          double alpha_lv0, double alpha_lv1, uint64_t seed, cudaStream_t stream) {
+                          double alpha_lv0, double alpha_lv1, const uint32_t key256[8], cudaStream_t stream) {
   KgArgs a{};
   a.tw_a = tw_a; a.tw_b = tw_b; a.s0 = d_s0; a.s1 = d_s1; a.s1_spec = d_s1_spec; a.bsk = d_bsk;
   a.n = n; a.l = l; a.bgbit = bgbit; a.alpha = alpha_lv1;
-  a.seed = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  for (int i = 0; i < 8; i++) a.seed.k[i] = key256[i];
+  ChaChaKey ksk_key = a.seed;
+  ksk_key.k[7] ^= 0x4B534B4Bu;   // independent stream for the key-switching key
   kg_s1_spectrum_kernel<<<1, 64, 0, stream>>>(a);
   kg_bsk_row_kernel<<<n * 2 * l, 64, 0, stream>>>(a);
   const uint32_t rows = br::kN * t * (1u << basebit);
-  kg_ksk_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(d_s0, d_s1, d_ksk_ref, n, basebit, t, alpha_lv0,
-                                                     make_uint2((uint32_t)seed ^ 0x5EEDu, (uint32_t)(seed >> 32)));
+  kg_ksk_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(d_s0, d_s1, d_ksk_ref, n, basebit, t, alpha_lv0, ksk_key);
   return cudaGetLastError();
 }

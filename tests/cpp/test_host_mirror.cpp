@@ -18,18 +18,18 @@ struct TestKeys {
   orc_rng rng;
 };
 
-static std::unique_ptr<TestKeys> make_keys(const SecurityParams &sp) {
+static std::unique_ptr<TestKeys> make_keys(const SecurityParams &sp, uint64_t seed = 0x5EED0001) {
   auto k = std::make_unique<TestKeys>();
   orc_params_by_name(sp.name, &k->p);
   k->s0.resize(sp.n); k->s1.resize(1024);
-  orc_secret_key(&k->p, 0x5EED0001, k->s0.data(), k->s1.data());
+  orc_secret_key(&k->p, seed, k->s0.data(), k->s1.data());
   k->ck.params = sp;
   k->ck.decomposition_offset = orc_decomposition_offset(&k->p);
   orc_gen_testvec(k->ck.blind_rotate_testvec.a, k->ck.blind_rotate_testvec.b);
   k->ck.key_switching_key.resize(orc_ksk_words(&k->p));
-  orc_gen_ksk(&k->p, k->s0.data(), k->s1.data(), 0x5EED0002, k->ck.key_switching_key.data());
+  orc_gen_ksk(&k->p, k->s0.data(), k->s1.data(), seed + 1, k->ck.key_switching_key.data());
   k->ck.bootstrapping_key.resize(orc_bsk_doubles(&k->p));
-  orc_gen_bsk(&k->p, k->s0.data(), k->s1.data(), 0x5EED0003, k->ck.bootstrapping_key.data(), nullptr);
+  orc_gen_bsk(&k->p, k->s0.data(), k->s1.data(), seed + 2, k->ck.bootstrapping_key.data(), nullptr);
   orc_rng_seed(&k->rng, 42);
   return k;
 }
@@ -110,6 +110,29 @@ int main() {
     Ciphertext nt = lb.bootstrap_func(c, [](size_t x) { return 1 - x; }, 2, k->ck);
     EXPECT(orc_lwe_decrypt_message(id.p.data(), k->s0.data(), k->p.n, 2) == (uint32_t)msg, "lut identity %d", msg);
     EXPECT(orc_lwe_decrypt_message(nt.p.data(), k->s0.data(), k->p.n, 2) == (uint32_t)(1 - msg), "lut not %d", msg);
+  }
+  // bootstrap_func can be called without bound (the reference builds and drops a table per call,
+  // lut.rs:49-65); explicit tables give their device slot back when dropped
+  {
+    Ciphertext c(k->p.n);
+    orc_lwe_encrypt_message(&k->p, 1, 2, k->s0.data(), &k->rng, c.p.data());
+    int wrong = 0;
+    for (int it = 0; it < 200; it++) {
+      Ciphertext r = lb.bootstrap_func(c, [it](size_t x) { return (x + it) & 1; }, 2, k->ck);
+      wrong += orc_lwe_decrypt_message(r.p.data(), k->s0.data(), k->p.n, 2) != (uint32_t)((1 + it) & 1);
+    }
+    EXPECT(wrong == 0, "%d of 200 bootstrap_func calls wrong", wrong);
+    for (int it = 0; it < 200; it++) {
+      LookupTable lut = engine->generate_lookup_table([](size_t x) { return x; }, 2, k->ck);
+      EXPECT(lut.lut_id > 0, "table %d got no slot", it);
+    }
+  }
+  // a DIFFERENT key at the SAME address must be re-uploaded (identity is by content, not pointer)
+  {
+    auto k2 = make_keys(SECURITY_128_BIT, 0x5EED0A01);
+    std::swap(k->ck, k2->ck); std::swap(k->s0, k2->s0); std::swap(k->s1, k2->s1);   // k->ck keeps its address, new content
+    EXPECT(dec(*k, strategy.bootstrap(enc(*k, true), k->ck)) == true, "rebind after key content change (true)");
+    EXPECT(dec(*k, strategy.bootstrap(enc(*k, false), k->ck)) == false, "rebind after key content change (false)");
   }
   printf(failures ? "FAILED (%d)\n" : "ALL OK\n", failures);
   return failures ? 1 : 0;

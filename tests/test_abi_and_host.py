@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     assert len(syms) >= 24
     for s in syms:
         assert hasattr(lib, s), s
-    assert lib.tfhe_abi_version() == 1
+    assert lib.tfhe_abi_version() == 2
 
 
 def test_library_is_sm100a_with_tma():

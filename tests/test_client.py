@@ -32,3 +32,20 @@ def test_client_and_oracle_interoperate():
     sk4 = SecretKey.new(T.SECURITY_UINT4, seed=8)
     c4 = Client(sk4, seed=9)
     assert np.array_equal(c4.decrypt_lwe_message(c4.encrypt_lwe_message(msgs, 16), 16), msgs)
+
+
+def test_os_entropy_rng_round_trip():
+    """seed=None: key bits, masks and noise come from os.urandom; encrypt -> decrypt still round-trips
+    and two keys differ."""
+    import rs_tfhe_b200 as T
+    from rs_tfhe_b200.client import Client, SecretKey
+    sk = SecretKey.new(T.SECURITY_128_BIT)
+    sk2 = SecretKey.new(T.SECURITY_128_BIT)
+    assert set(np.unique(sk.key_lv0)) <= {0, 1} and not np.array_equal(sk.key_lv0, sk2.key_lv0)
+    c = Client(sk)
+    bits = np.array([0, 1, 1, 0, 1], dtype=bool)
+    assert np.array_equal(c.decrypt_bool(c.encrypt_bool(bits)), bits)
+    m = np.arange(16)
+    assert np.array_equal(c.decrypt_lwe_message(c.encrypt_lwe_message(m, 16), 16), m)
+    noise = c.rng.normal(0.0, 1.0, 20000)
+    assert abs(noise.mean()) < 0.05 and abs(noise.std() - 1.0) < 0.05

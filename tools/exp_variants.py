@@ -32,9 +32,13 @@ count = sys.argv[2] if len(sys.argv) > 2 else "14208"
 out = {}
 for v in variants:
     env = dict(os.environ, TFHE_BR_VARIANT=v, TFHE_BR_LATENCY_MAX="0")
-    p = subprocess.run([sys.executable, __file__, "--child", count], env=env, capture_output=True, text=True, timeout=900)
-    line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
-    out[v] = json.loads(line[0][7:]) if line else {"error": (p.stderr or p.stdout)[-600:]}
+    try:
+        p = subprocess.run([sys.executable, __file__, "--child", count], env=env, capture_output=True, text=True,
+                           timeout=int(os.environ.get("EXP_TIMEOUT", "240")))
+        line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
+        out[v] = json.loads(line[0][7:]) if line else {"error": (p.stderr or p.stdout)[-600:]}
+    except subprocess.TimeoutExpired:
+        out[v] = {"error": "timeout (hang?)"}
     print(v, out[v], flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "exp_variants.json"), "w"), indent=1)
