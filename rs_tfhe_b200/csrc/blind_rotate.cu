@@ -26,7 +26,7 @@ using namespace br;
 #define BR_PRODUCER_SLEEP_NS 256
 #endif
 #ifndef BR_DEFAULT_VARIANT
-#define BR_DEFAULT_VARIANT 9
+#define BR_DEFAULT_VARIANT 8
 #endif
 
 namespace {
@@ -1283,14 +1283,42 @@ int br_latency_threshold(int num_sms) {
   return thr >= 0 ? thr : num_sms;  // measured crossover: 148 gates 2.55 vs 4.04 ms, 296 gates 5.04 vs 4.41 ms
 }
 
+// ciphertexts [base, base + n) of a launch
+BrArgs br_slice(const BrArgs &a, size_t base, size_t n) {
+  BrArgs s = a;
+  const size_t w = a.n + 1;
+  const bool gate = a.op >= 0 || a.ops;
+  s.in = a.in + base * (gate ? 2 * w : w);
+  if (a.ops) s.ops = a.ops + base;
+  if (a.tv_index) s.tv_index = a.tv_index + base;
+  const size_t out_words = a.out_mode == BR_OUT_TRLWE ? 2 * (size_t)kN
+                           : a.out_mode == BR_OUT_EXTRACT ? (size_t)kN + 1 : w;
+  s.out = a.out + base * out_words;
+  s.count = n;
+  return s;
+}
+
 template <int L, int BGBIT>
 cudaError_t launch_t(const BrArgs &args, int num_sms, cudaStream_t stream) {
   if (L > 1 && args.count <= (size_t)br_latency_threshold(num_sms))
     return launch_latency<L, BGBIT>(args, num_sms, stream);
-  // 9 (default): 128 threads per ciphertext, all-FMA radix 4/8/4/4 passes (blind_rotate_s.cu)
+  // 9: 128 threads per ciphertext, all-FMA radix 4/8/4/4 passes (blind_rotate_s.cu), every round
   if (br_variant() == 9) return br_launch_s(L, BGBIT, args, num_sms, stream);
-  // 8: 64 threads per ciphertext, pass B<->C exchange through tensor memory + one shuffle stage (permuted key layout)
-  if (br_variant() == 8) return launch_x<L, BGBIT, true>(args, num_sms, stream);
+  // 8 (default): full persistent rounds (4 ciphertexts per SM) on the 64-thread kernel -- pass B<->C
+  // exchange through tensor memory + one shuffle stage, permuted key layout -- and a last round that
+  // fills at most 3 of the 4 slots per SM on the 128-thread kernel, which is faster at partial residency
+  // (B200, one round of 148/296/444/592 ciphertexts: 2.76/3.63/4.65/5.86 ms against 4.34/4.43/5.70/5.67 ms).
+  if (br_variant() == 8) {
+    const size_t round = (size_t)num_sms * 4;
+    const size_t full = args.count / round * round, tail = args.count - full;
+    if (tail == 0 || tail > (size_t)num_sms * 3 || !args.bsk3)
+      return launch_x<L, BGBIT, true>(args, num_sms, stream);
+    if (full) {
+      cudaError_t e = launch_x<L, BGBIT, true>(br_slice(args, 0, full), num_sms, stream);
+      if (e != cudaSuccess) return e;
+    }
+    return br_launch_s(L, BGBIT, br_slice(args, full, tail), num_sms, stream);
+  }
   // 7: variant 3 with the 2^52-bias conversions
   if (br_variant() == 7) return launch_v<L, BGBIT, 4, 4, 3, true, 232, 40, false, true>(args, num_sms, stream);
   if (br_variant() == 4) return launch_v4<L, BGBIT>(args, num_sms, stream);
@@ -1308,7 +1336,7 @@ cudaError_t launch_t(const BrArgs &args, int num_sms, cudaStream_t stream) {
 }  // namespace
 
 bool br_uses_permuted_key() { return br_variant() == 8; }
-bool br_uses_s_key() { return br_variant() == 9; }
+bool br_uses_s_key() { return br_variant() == 9 || br_variant() == 8; }
 
 bool br_supported(uint32_t l, uint32_t bgbit) {
   return (l == 3 && bgbit == 6) || (l == 2 && bgbit == 10) || (l == 1 && bgbit == 18) ||
@@ -1316,7 +1344,13 @@ bool br_supported(uint32_t l, uint32_t bgbit) {
 }
 
 cudaError_t br_launch(uint32_t l, uint32_t bgbit, const BrArgs &args, int num_sms,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, int *launched) {
+  if (launched) {   // kernels this call puts on the stream (the default shape may split off a tail launch)
+    const size_t round = (size_t)num_sms * 4, tail = args.count % round;
+    const bool split = br_variant() == 8 && args.count > round && tail != 0 && tail <= (size_t)num_sms * 3 &&
+                       args.bsk3 && !(l > 1 && args.count <= (size_t)br_latency_threshold(num_sms));
+    *launched = args.count == 0 ? 0 : split ? 2 : 1;
+  }
   if (args.count == 0) return cudaSuccess;
   if (l == 3 && bgbit == 6) return launch_t<3, 6>(args, num_sms, stream);
   if (l == 2 && bgbit == 10) return launch_t<2, 10>(args, num_sms, stream);

@@ -48,16 +48,7 @@ constexpr int kThreads = kConsumers + 128;        // + a producer warpgroup (one
 // (480 - 24) / 4 = 114 -> 112.  (Asking for 120 blocks forever: measured, the kernel hangs.)
 constexpr int kRegsCons = 112, kRegsProd = 24;
 
-#ifdef TFHE_S_ABLATION_BUILD
-__device__ unsigned long long g_trace[16 * 4 * 16];   // [warp][step 100..103][point]
-#define TRACE(pt)                                                                              \
-  if ((ABL & 8) && blockIdx.x == 0 && rd == 0 && i >= 100 && i < 104 && lane == 0)             \
-    g_trace[(warp * 4 + (i - 100)) * 16 + (pt)] = clock64();
-#else
-#define TRACE(pt)
-#endif
-
-template <int L, int BGBIT, int STAGES, bool MAGIC, int ABL = 0>
+template <int L, int BGBIT, int STAGES, bool MAGIC>
 __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel_s(const BrArgs args) {
   constexpr int L2 = 2 * L;
   constexpr bool EXACT = (L == 3 && BGBIT == 6);
@@ -130,12 +121,6 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel_s(const BrArg
     }
     tm_wait_st();
   }
-  // De-phase the four ciphertexts of the CTA: a sub-partition hosts one warp of each, and four warps in
-  // the same phase leave the FP64 pipe idle whenever they all reach an integer / exchange stretch together.
-  if (args.stagger) {
-    const long long until = clock64() + (long long)args.stagger * g;
-    while (clock64() < until) __nanosleep(64);
-  }
   uint32_t stage = 0, parity = 0;
   for (uint32_t rd = 0; rd < rounds; rd++) {
     const size_t ct = ((size_t)rd * kG + g) * grid + blockIdx.x;
@@ -145,7 +130,6 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel_s(const BrArg
     for (uint32_t i = 0; i < n; i++) {
       if (active) {
         cplx racc[2][4];
-        TRACE(0)
         const uint32_t abar = abar_s[i];
 #pragma unroll
         for (int o = 0; o < 2; o++)
@@ -159,43 +143,33 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel_s(const BrArg
 #pragma unroll
             for (int d = 0; d < L; d++) brs::fwd_pass_a<BGBIT, MAGIC>(T, d, t_re, t_im, exch + d * kHalf);
           }
-          TRACE(1 + 5 * p)
           named_sync<brs::kT>(g + 1);
-          TRACE(2 + 5 * p)
 #pragma unroll
           for (int d = 0; d < L; d++) {
             cplx y[4];
             {
               cplx tb[4];
-              if (ABL & 2) { for (int k = 0; k < 4; k++) tb[k] = mk(0.5 + T * 1e-3, 0.25 + k); } else tm_load4(t_b, tb);
+              tm_load4(t_b, tb);
               brs::fwd_pass_b(T, exch + d * kHalf, tb[0], tb[1], tb[2], y);
             }
-            if (!(ABL & 1)) xchg_fwd(tq0, y);
+            xchg_fwd(tq0, y);
             cplx tcd[4];
-            if (ABL & 2) { for (int k = 0; k < 4; k++) tcd[k] = mk(0.5 + T * 1e-3, 0.25 + k); } else tm_load4(t_cd, tcd);
+            tm_load4(t_cd, tcd);
             brs::r4<false>(y, tcd[0], tcd[1]);
-            if (!(ABL & 1)) xchg_fwd(tq1, y);
+            xchg_fwd(tq1, y);
             brs::r4<false>(y, tcd[2], tcd[3]);
             mbar_wait(&full[stage], parity);
             const cplx *row = ring + stage * brs::kRowCplx + T;
 #pragma unroll
             for (int kd = 0; kd < 4; kd++) {
-              if (ABL & 4) {   // no key reads from shared memory
-                cfma(racc[0][kd], y[kd], mk(0.5 + kd, 1e-3 * T));
-                cfma(racc[1][kd], y[kd], mk(0.25 + kd, 2e-3 * T));
-              } else {
-                cfma(racc[0][kd], y[kd], row[(kd * 2 + 0) * brs::kT]);
-                cfma(racc[1][kd], y[kd], row[(kd * 2 + 1) * brs::kT]);
-              }
+              cfma(racc[0][kd], y[kd], row[(kd * 2 + 0) * brs::kT]);
+              cfma(racc[1][kd], y[kd], row[(kd * 2 + 1) * brs::kT]);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[stage]);
             if (++stage == STAGES) { stage = 0; parity ^= 1; }
-            if (d == 0) { TRACE(3 + 5 * p) }
           }
-          TRACE(4 + 5 * p)
           named_sync<brs::kT>(g + 1);   // everyone has read this polynomial's pass-A output
-          TRACE(5 + 5 * p)
         }
         {
           cplx ti[4];
@@ -203,16 +177,14 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel_s(const BrArg
 #pragma unroll
           for (int o = 0; o < 2; o++) {
             brs::r4_plain<true>(racc[o]);
-            if (!(ABL & 1)) xchg_inv(tq0, racc[o]);
+            xchg_inv(tq0, racc[o]);
             brs::r4<true>(racc[o], ti[0], ti[1]);
-            if (!(ABL & 1)) xchg_inv(tq1, racc[o]);
+            xchg_inv(tq1, racc[o]);
             brs::r4<true>(racc[o], ti[2], ti[3]);
             brs::inv_store_b(T, racc[o], exch + o * (8 * brs::kInvPitch));
           }
         }
-        TRACE(11)
         named_sync<brs::kT>(g + 1);
-        TRACE(12)
         {
           cplx ta[4], ut[4];
           tm_load4(t_ai, ta);
@@ -221,9 +193,7 @@ __global__ void __launch_bounds__(kThreads, 1) blind_rotate_kernel_s(const BrArg
           for (int o = 0; o < 2; o++)
             brs::inv_pass_a<EXACT, MAGIC>(T, exch + o * (8 * brs::kInvPitch), ta[0], ta[1], ta[2], ut, acc + o * kN);
         }
-        TRACE(13)
         named_sync<brs::kT>(g + 1);
-        TRACE(14)
       } else {
         // idle group: keep the ring's phase accounting in lock step
         for (int c = 0; c < L2; c++) {
@@ -247,22 +217,8 @@ template <int L, int BGBIT, int STAGES>
 cudaError_t launch_s(const BrArgs &args_in, int num_sms, cudaStream_t stream) {
   constexpr bool MAGIC = (L == 3 && BGBIT == 6);
   if (!args_in.bsk3 || !args_in.tw_s) return cudaErrorInvalidValue;   // engine did not build this kernel's key order
-  BrArgs args = args_in;
-  static const int stagger = [] { const char *e = getenv("TFHE_S_STAGGER"); return e ? atoi(e) : 0; }();
-  args.stagger = (uint32_t)stagger;
-  static const int abl = [] { const char *e = getenv("TFHE_S_ABLATE"); return e ? atoi(e) : 0; }();
+  const BrArgs &args = args_in;
   auto kern = blind_rotate_kernel_s<L, BGBIT, STAGES, MAGIC>;
-#ifdef TFHE_S_ABLATION_BUILD
-  if (L == 3 && STAGES == 4) {
-    if (abl == 1) kern = blind_rotate_kernel_s<L, BGBIT, STAGES, MAGIC, 1>;
-    if (abl == 2) kern = blind_rotate_kernel_s<L, BGBIT, STAGES, MAGIC, 2>;
-    if (abl == 3) kern = blind_rotate_kernel_s<L, BGBIT, STAGES, MAGIC, 3>;
-    if (abl == 4) kern = blind_rotate_kernel_s<L, BGBIT, STAGES, MAGIC, 4>;
-    if (abl == 7) kern = blind_rotate_kernel_s<L, BGBIT, STAGES, MAGIC, 7>;
-    if (abl == 8) kern = blind_rotate_kernel_s<L, BGBIT, STAGES, MAGIC, 8>;
-  }
-#endif
-  (void)abl;
   constexpr int kInvBytes = 8 * brs::kInvPitch * 16, kFwdBytes = kHalf * 16;
   constexpr int kExchBytes = (L * kFwdBytes > 2 * kInvBytes) ? L * kFwdBytes : 2 * kInvBytes;
   const int smem = STAGES * kStageBytes + kG * (2 * kN * 4 + kExchBytes + 2432) + 2 * STAGES * 8 + 16;
@@ -276,16 +232,9 @@ cudaError_t launch_s(const BrArgs &args_in, int num_sms, cudaStream_t stream) {
 
 }  // namespace
 
-#ifdef TFHE_S_ABLATION_BUILD
-extern "C" int tfhe_debug_read_trace(unsigned long long *out) {
-  return (int)cudaMemcpyFromSymbol(out, g_trace, sizeof(g_trace));
-}
-#endif
-
 cudaError_t br_launch_s(uint32_t l, uint32_t bgbit, const BrArgs &args, int num_sms, cudaStream_t stream) {
   if (args.count == 0) return cudaSuccess;
-  static const int stages = [] { const char *e = getenv("TFHE_S_STAGES"); return e ? atoi(e) : 4; }();
-  if (l == 3 && bgbit == 6) return stages == 5 ? launch_s<3, 6, 5>(args, num_sms, stream) : launch_s<3, 6, 4>(args, num_sms, stream);
+  if (l == 3 && bgbit == 6) return launch_s<3, 6, 4>(args, num_sms, stream);
   if (l == 2 && bgbit == 10) return launch_s<2, 10, 4>(args, num_sms, stream);
   if (l == 1 && bgbit == 18) return launch_s<1, 18, 4>(args, num_sms, stream);
   if (l == 1 && bgbit == 22) return launch_s<1, 22, 4>(args, num_sms, stream);

@@ -64,6 +64,20 @@ struct Scratch {
   void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
 };
 
+struct PinnedScratch {
+  void *p = nullptr;
+  size_t bytes = 0;
+  cudaError_t reserve(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; bytes = 0;
+    cudaError_t e = cudaHostAlloc(&p, need, cudaHostAllocDefault);
+    if (e == cudaSuccess) bytes = need;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; bytes = 0; }
+};
+
 }  // namespace
 
 struct tfhe_engine {
@@ -92,6 +106,11 @@ struct tfhe_engine {
   // two pipeline slots: H2D of chunk k+1 and D2H of chunk k-1 overlap the kernels of chunk k
   struct Slot {
     Scratch in, ext, out, ops, idx;
+    // pinned staging for callers whose buffers are pageable (a Rust Vec<Ciphertext> is): the host thread
+    // copies chunk k+1 into hin while the GPU runs chunk k, and drains hout after the chunk's D2H
+    PinnedScratch hin, hout;
+    void *drain_dst = nullptr;       // pending hout -> caller copy
+    size_t drain_bytes = 0;
     cudaEvent_t h2d_done = nullptr, br_start = nullptr, br_end = nullptr, ks_end = nullptr,
                 d2h_done = nullptr;
     bool busy = false;
@@ -99,6 +118,7 @@ struct tfhe_engine {
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float last_ms[2] = {0.f, 0.f};
+  float dev_ms[2] = {0.f, 0.f};   // device-pointer path: kernel time of the chunks already retired in this call
   uint64_t launches = 0;
   // multi-GPU (tfhe_engine_create_multi): this engine is device_ids[0]; peers are the other devices'
   // engines, owned here.  The cloud key is broadcast root -> peers with NCCL at key-load time; batch
@@ -256,8 +276,9 @@ int run_device(tfhe_engine *e, tfhe_engine::Slot &sl, int op, const uint8_t *d_o
     a.out_mode = out_kind == 1 ? BR_OUT_EXTRACT2 : BR_OUT_TRLWE;
   }
   CU(cudaEventRecord(sl.br_start, e->stream));
-  CU(br_launch(e->p.l, e->p.bgbit, a, e->num_sms, e->stream));
-  e->launches++;
+  int n_br = 0;
+  CU(br_launch(e->p.l, e->p.bgbit, a, e->num_sms, e->stream, &n_br));
+  e->launches += (uint64_t)n_br;
   CU(cudaEventRecord(sl.br_end, e->stream));
   if (out_kind == 0) {
     int rc = key_switch(e, static_cast<const uint32_t *>(sl.ext.p), d_out, count);
@@ -271,6 +292,10 @@ int run_device(tfhe_engine *e, tfhe_engine::Slot &sl, int op, const uint8_t *d_o
 int retire_slot(tfhe_engine::Slot &sl, float &ms0, float &ms1) {
   if (!sl.busy) return TFHE_OK;
   CU(cudaEventSynchronize(sl.d2h_done));
+  if (sl.drain_dst) {
+    memcpy(sl.drain_dst, sl.hout.p, sl.drain_bytes);
+    sl.drain_dst = nullptr;
+  }
   float t0 = 0.f, t1 = 0.f;
   CU(cudaEventElapsedTime(&t0, sl.br_start, sl.br_end));
   CU(cudaEventElapsedTime(&t1, sl.br_end, sl.ks_end));
@@ -307,6 +332,15 @@ int run_host_locked(tfhe_engine *e, int op, const uint8_t *ops, int lut_id, cons
   // one (likewise its download).
   const size_t round = (size_t)e->num_sms * 4;
   const size_t chunk = round * 28, edge = round * 4;
+  // Pageable caller buffers (the normal case for a drop-in caller) go through the pinned staging ring
+  // when the call spans several chunks; a pinned / registered buffer is copied from directly.
+  auto pageable = [](const void *ptr) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+  };
+  const bool stage_in = count > 2 * edge && pageable(in);
+  const bool stage_out = count > 2 * edge && pageable(out);
   // order after whatever the caller queued on the engine stream
   CU(cudaEventRecord(e->ev[3], e->stream));
   CU(cudaStreamWaitEvent(e->copy_in, e->ev[3], 0));
@@ -322,8 +356,13 @@ int run_host_locked(tfhe_engine *e, int op, const uint8_t *ops, int lut_id, cons
     if (rc != TFHE_OK) return rc;
     CU(sl.in.reserve(c * in_words * 4));
     CU(sl.out.reserve(c * out_words * 4));
-    CU(cudaMemcpyAsync(sl.in.p, in + base * in_words, c * in_words * 4, cudaMemcpyHostToDevice,
-                       e->copy_in));
+    const void *h_src = in + base * in_words;
+    if (stage_in) {
+      CU(sl.hin.reserve(chunk * in_words * 4));
+      memcpy(sl.hin.p, h_src, c * in_words * 4);   // overlaps the previous chunk's kernels
+      h_src = sl.hin.p;
+    }
+    CU(cudaMemcpyAsync(sl.in.p, h_src, c * in_words * 4, cudaMemcpyHostToDevice, e->copy_in));
     const uint8_t *d_ops = nullptr;
     if (ops) {
       CU(sl.ops.reserve(c));
@@ -342,8 +381,14 @@ int run_host_locked(tfhe_engine *e, int op, const uint8_t *ops, int lut_id, cons
                     static_cast<uint32_t *>(sl.out.p), c, out_kind, d_ids);
     if (rc != TFHE_OK) return rc;
     CU(cudaStreamWaitEvent(e->copy_out, sl.ks_end, 0));
-    CU(cudaMemcpyAsync(out + base * out_words, sl.out.p, c * out_words * 4, cudaMemcpyDeviceToHost,
-                       e->copy_out));
+    void *h_dst = out + base * out_words;
+    if (stage_out) {
+      CU(sl.hout.reserve(chunk * out_words * 4));
+      sl.drain_dst = h_dst;
+      sl.drain_bytes = c * out_words * 4;
+      h_dst = sl.hout.p;
+    }
+    CU(cudaMemcpyAsync(h_dst, sl.out.p, c * out_words * 4, cudaMemcpyDeviceToHost, e->copy_out));
     CU(cudaEventRecord(sl.d2h_done, e->copy_out));
     sl.busy = true;
   }
@@ -637,6 +682,7 @@ void tfhe_engine_destroy(tfhe_engine *e) {
   e->s_misc.release();
   for (auto &sl : e->slot) {
     sl.in.release(); sl.ext.release(); sl.out.release(); sl.ops.release(); sl.idx.release();
+    sl.hin.release(); sl.hout.release();
     for (cudaEvent_t pe : {sl.h2d_done, sl.br_start, sl.br_end, sl.ks_end, sl.d2h_done})
       if (pe) cudaEventDestroy(pe);
   }
@@ -1196,6 +1242,18 @@ int tfhe_batch_reencrypt(tfhe_engine *e, const tfhe_reenc_key *key, const uint32
   return TFHE_OK;
 }
 
+// The device path re-records slot 0's events per chunk: before the next chunk is queued the finished
+// one's kernel times are added to the running totals (tfhe_engine_synchronize adds the last chunk).
+static int dev_retire_chunk(tfhe_engine *e) {
+  tfhe_engine::Slot &sl = e->slot[0];
+  CU(cudaEventSynchronize(sl.ks_end));
+  float t0 = 0.f, t1 = 0.f;
+  CU(cudaEventElapsedTime(&t0, sl.br_start, sl.br_end));
+  CU(cudaEventElapsedTime(&t1, sl.br_end, sl.ks_end));
+  e->dev_ms[0] += t0; e->dev_ms[1] += t1;
+  return TFHE_OK;
+}
+
 int tfhe_batch_gate_dev(tfhe_engine *e, tfhe_gate op, const uint8_t *d_ops,
                         const uint32_t *d_in_pairs, uint32_t *d_out, size_t count) {
   if (!e) return fail(TFHE_ERR_INVALID, "null engine");
@@ -1205,8 +1263,10 @@ int tfhe_batch_gate_dev(tfhe_engine *e, tfhe_gate op, const uint8_t *d_ops,
   std::lock_guard<std::mutex> lock(e->mu);
   CU(cudaSetDevice(e->dev));
   const size_t w = e->p.n + 1;
+  e->dev_ms[0] = e->dev_ms[1] = 0.f;
   for (size_t base = 0; base < count; base += kChunk) {
     size_t c = count - base < kChunk ? count - base : kChunk;
+    if (base) { int rc = dev_retire_chunk(e); if (rc != TFHE_OK) return rc; }
     int rc = run_device(e, e->slot[0], d_ops ? 0 : (int)op, d_ops ? d_ops + base : nullptr, -1,
                         d_in_pairs + base * 2 * w, d_out + base * w, c, 0);
     if (rc != TFHE_OK) return rc;
@@ -1225,8 +1285,10 @@ int tfhe_batch_bootstrap_dev(tfhe_engine *e, int lut_id, const uint32_t *d_in, u
     if (lut_id < 0) return fail(TFHE_ERR_INVALID, "unknown or stale lut id");
   }
   const size_t w = e->p.n + 1;
+  e->dev_ms[0] = e->dev_ms[1] = 0.f;
   for (size_t base = 0; base < count; base += kChunk) {
     size_t c = count - base < kChunk ? count - base : kChunk;
+    if (base) { int rc = dev_retire_chunk(e); if (rc != TFHE_OK) return rc; }
     int rc = run_device(e, e->slot[0], -1, nullptr, lut_id, d_in + base * w, d_out + base * w, c,
                         key_switch ? 0 : 1);
     if (rc != TFHE_OK) return rc;
@@ -1241,7 +1303,8 @@ int tfhe_engine_synchronize(tfhe_engine *e) {
   float t0 = 0.f, t1 = 0.f;
   if (cudaEventElapsedTime(&t0, e->slot[0].br_start, e->slot[0].br_end) == cudaSuccess &&
       cudaEventElapsedTime(&t1, e->slot[0].br_end, e->slot[0].ks_end) == cudaSuccess) {
-    e->last_ms[0] = t0; e->last_ms[1] = t1;
+    e->last_ms[0] = e->dev_ms[0] + t0; e->last_ms[1] = e->dev_ms[1] + t1;
+    e->dev_ms[0] = e->dev_ms[1] = 0.f;
   } else {
     cudaGetLastError();
   }

@@ -28,13 +28,12 @@ struct BrArgs {
   uint32_t n;
   uint32_t offset;          // CloudKey.decomposition_offset, used verbatim
   size_t count;
-  uint32_t stagger;         // 128-thread kernel: start offset between the CTA's ciphertext groups, in cycles
 };
 bool br_supported(uint32_t l, uint32_t bgbit);
 bool br_uses_permuted_key();  // the selected throughput kernel reads BrArgs::bsk2
 bool br_uses_s_key();         // the selected throughput kernel reads BrArgs::bsk3 / tw_s
 cudaError_t br_launch(uint32_t l, uint32_t bgbit, const BrArgs &args, int num_sms,
-                      cudaStream_t stream);
+                      cudaStream_t stream, int *launched = nullptr);
 // 128-thread-per-ciphertext throughput kernel (blind_rotate_s.cu)
 cudaError_t br_launch_s(uint32_t l, uint32_t bgbit, const BrArgs &args, int num_sms,
                         cudaStream_t stream);

@@ -195,12 +195,17 @@ def test_blind_rotate_other_gadgets_p2(name, m):
     lut_id, lut_b = e.lut_generate(table, m)
     assert np.array_equal(lut_b, O.lut_generate(table, m))
     bound = 0.25 / m                                # half of a message slot half-width
-    for count in (5, 601):
+    for count in (5, 601):                          # 601 = one full round (64-thread kernel) + a tail of 9 (128-thread)
         msgs = np.arange(count) % m
         cts = K.encrypt_message(msgs, m, rng)
         got = e.batch_bootstrap_lut(lut_id, cts)
-        assert np.array_equal(K.decrypt_message(got, m), (3 * msgs + 1) % m), (name, count)
-        ref = K.batch_bootstrap(cts[:5], key_switch=True, lut_b=lut_b)
-        d = torus_dist(K.phase(got[:5]), K.phase(ref))
-        assert d.max() < bound, (name, count, d.max())
+        ref = K.batch_bootstrap(cts, key_switch=True, lut_b=lut_b)
+        d = torus_dist(K.phase(got), K.phase(ref))
+        assert d.max() < bound, (name, count, d.max())             # same phase as the oracle, every ciphertext
+        dec_g, dec_r = K.decrypt_message(got, m), K.decrypt_message(ref, m)
+        # the algorithm itself mis-decodes a message now and then at the larger moduli (input modulus
+        # switch noise vs slot width); GPU and oracle must agree, and both be mostly right
+        assert (dec_g != dec_r).mean() <= 0.01, (name, count)
+        if m <= 32:   # at m = 128 the input modulus switch alone (sigma 3.4e-3 vs slot half-width 2e-3) decodes
+            assert (dec_g == (3 * msgs + 1) % m).mean() >= 0.97, (name, count)   # wrongly most of the time, oracle included
     e.close()

@@ -1,0 +1,38 @@
+"""C5 through the in-library multi-GPU engine (one process, tfhe_engine_create_multi): 1 048 576 mixed
+gates sharded over all visible GPUs, host buffers (pageable), plus the timed cloud-key broadcast.
+usage: multi_bench.py [total_gates] [n_devices]"""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import rs_tfhe_b200 as T
+sys.path.insert(0, ROOT)
+from bench import synthetic_cloud_key
+
+total = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
+n_dev = int(sys.argv[2]) if len(sys.argv) > 2 else T.device_count()
+P = T.PARAMS_BY_NAME["128"]
+res = {"total_gates": total}
+block = 65536
+r = np.random.default_rng(0x5EED0005)
+pairs = np.tile(r.integers(0, 2**32, (block, 2, P.n + 1), dtype=np.uint32), (total // block, 1, 1))
+ops = r.integers(0, 6, total).astype(np.uint8)            # the 6 batchable gates, uniform per element
+ck = synthetic_cloud_key(T, P, 1234)
+base = None
+for nd in sorted({1, n_dev}):
+    e = T.CudaBootstrap(P, list(range(nd)))
+    e.load_cloud_key(ck)
+    e.load_cloud_key(ck)                                   # second load: communicator already warm
+    out = e.batch_gate_mixed(ops[:4096 * nd], pairs[:4096 * nd])   # warm-up (allocations)
+    t = time.perf_counter()
+    out = e.batch_gate_mixed(ops, pairs)
+    dt = time.perf_counter() - t
+    crc = int(out[:, -1].astype(np.uint64).sum() & 0xFFFFFFFF)
+    res[f"gpus_{nd}"] = {"seconds": dt, "gates_per_s": total / dt, "key_broadcast_ms_warm": e.last_broadcast_ms(),
+                         "result_checksum": crc, "kernel_ms_slowest_device": e.last_kernel_ms()}
+    base = base or dt
+    res[f"gpus_{nd}"]["speedup_vs_1"] = base / dt
+    e.close()
+print(json.dumps(res))
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+json.dump(res, open(os.path.join(ROOT, "gpurun_out", "multi_bench.json"), "w"), indent=1)
