@@ -227,6 +227,30 @@ void tfhe_reenc_key_destroy(tfhe_reenc_key *k);
 int tfhe_batch_reencrypt(tfhe_engine *e, const tfhe_reenc_key *key, const uint32_t *in /*[count][n+1]*/,
                          uint32_t *out /*[count][n+1]*/, size_t count);
 
+/* ---- next to the path: levelised boolean circuits -------------------------------------
+ * The reference evaluates circuits gate by gate through gates::Gates (examples/add_two_numbers.rs:11-49,
+ * src/gates.rs:157-199 mux / mux_naive, src/circuits.rs compare_bit).  A tfhe_circuit records the same
+ * gates over integer wire ids; tfhe_circuit_run splits it into levels of independent bootstraps and runs
+ * each level as ONE device batch over `batch` independent input sets, wires resident in HBM (gather
+ * kernel -> blind rotation -> [mux combine] -> key switch).  NOT and constants are free (resolved while
+ * gathering).  tfhe_circuit_mux is the SOUND fused multiplexer: AND(sel, a) and AND(!sel, b) are blind-
+ * rotated, extracted at level 1 with the ring's real degree, added with the OR offset, and key-switched
+ * once -- what Gates::mux (gates.rs:157-183) intends (its sample_extract_index_2 is wrong). */
+typedef struct tfhe_circuit tfhe_circuit;
+int tfhe_circuit_create(tfhe_engine *e, tfhe_circuit **out);
+void tfhe_circuit_destroy(tfhe_circuit *c);
+int tfhe_circuit_input(tfhe_circuit *c, uint32_t *wire_out);
+int tfhe_circuit_constant(tfhe_circuit *c, int value, uint32_t *wire_out);            /* gates.rs:212-218 */
+int tfhe_circuit_not(tfhe_circuit *c, uint32_t a, uint32_t *wire_out);               /* gates.rs:202-204 */
+int tfhe_circuit_gate(tfhe_circuit *c, tfhe_gate op, uint32_t a, uint32_t b, uint32_t *wire_out);
+int tfhe_circuit_mux(tfhe_circuit *c, uint32_t sel, uint32_t then_wire, uint32_t else_wire, uint32_t *wire_out);
+int tfhe_circuit_output(tfhe_circuit *c, uint32_t wire);
+/* depth in bootstrap levels, blind rotations and key switches per input set */
+int tfhe_circuit_stats(tfhe_circuit *c, uint32_t *levels, uint32_t *bootstraps, uint32_t *key_switches);
+/* inputs u32[n_inputs][batch][n+1] (input order = tfhe_circuit_input order), outputs
+ * u32[n_outputs][batch][n+1] (tfhe_circuit_output order); host buffers. */
+int tfhe_circuit_run(tfhe_circuit *c, const uint32_t *inputs, uint32_t *outputs, size_t batch);
+
 /* ---- the hot path, device-resident buffers (no copies; asynchronous on the
  *      engine stream).  Pointers are CUDA device pointers on the engine's GPU. */
 int tfhe_batch_gate_dev(tfhe_engine *e, tfhe_gate op, const uint8_t *d_ops /*NULL or [count]*/,

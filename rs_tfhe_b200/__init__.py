@@ -148,6 +148,18 @@ def _load():
     L.tfhe_batch_ifft.argtypes = [vp, u32p, vp, C.c_size_t]
     L.tfhe_batch_fft.argtypes = [vp, vp, u32p, C.c_size_t]
     L.tfhe_batch_poly_mul.argtypes = [vp, u32p, u32p, u32p, C.c_size_t]
+    L.tfhe_circuit_create.argtypes = [vp, C.POINTER(vp)]
+    L.tfhe_circuit_destroy.argtypes = [vp]
+    L.tfhe_circuit_destroy.restype = None
+    u32o = C.POINTER(C.c_uint32)
+    L.tfhe_circuit_input.argtypes = [vp, u32o]
+    L.tfhe_circuit_constant.argtypes = [vp, C.c_int, u32o]
+    L.tfhe_circuit_not.argtypes = [vp, C.c_uint32, u32o]
+    L.tfhe_circuit_gate.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint32, u32o]
+    L.tfhe_circuit_mux.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, u32o]
+    L.tfhe_circuit_output.argtypes = [vp, C.c_uint32]
+    L.tfhe_circuit_stats.argtypes = [vp, u32o, u32o, u32o]
+    L.tfhe_circuit_run.argtypes = [vp, vp, vp, C.c_size_t]
     L.tfhe_lut_release.argtypes = [vp, C.c_int]
     L.tfhe_batch_bootstrap_func.argtypes = [vp, u32p, C.c_uint32, C.c_double, u32p, u32p, C.c_size_t]
     L.tfhe_batch_bootstrap_lut.argtypes = [vp, C.c_int, u32p, u32p, C.c_size_t]

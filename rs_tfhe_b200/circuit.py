@@ -3,9 +3,9 @@
 The reference evaluates circuits gate by gate (examples/add_two_numbers.rs:11-49: a ripple-carry
 adder built from `xor`, `and`, `or`).  Here a circuit is recorded once, split into levels of
 mutually independent bootstrapped gates, and every level goes to the device as ONE mixed-gate
-batch (`tfhe_batch_gate_dev` with per-element gate codes) over all `batch` independent input
-sets; the wires stay resident in HBM between levels (torch is used only for the gather/scatter
-plumbing and the free linear gates NOT/COPY).
+batch over all `batch` independent input sets; the wires stay resident in HBM between levels.
+Recording and the adder / comparator builders live here; scheduling and execution are the library's
+`tfhe_circuit_*` entry points (csrc/circuit.cuh): device-side gather, no torch.
 """
 from __future__ import annotations
 
@@ -14,16 +14,19 @@ from typing import Dict, List, Sequence, Tuple
 
 import numpy as np
 
-from . import GATES, CudaBootstrap, f64_to_torus
+import ctypes as C
+
+from . import GATES, CudaBootstrap, _check, _load
 
 _CODE = {g: i for i, g in enumerate(GATES)}
 
 
 @dataclass
 class _Gate:
-    op: str                  # a GATES name, or "NOT" / "COPY" / "CONST0" / "CONST1" / "INPUT"
+    op: str                  # a GATES name, or "NOT" / "COPY" / "CONST0" / "CONST1" / "INPUT" / "MUX"
     a: int = -1
     b: int = -1
+    c: int = -1
 
 
 @dataclass
@@ -33,8 +36,8 @@ class Circuit:
     inputs: List[int] = field(default_factory=list)
     outputs: List[int] = field(default_factory=list)
 
-    def _add(self, op: str, a: int = -1, b: int = -1) -> int:
-        self.gates.append(_Gate(op, a, b))
+    def _add(self, op: str, a: int = -1, b: int = -1, c: int = -1) -> int:
+        self.gates.append(_Gate(op, a, b, c))
         return len(self.gates) - 1
 
     def input(self) -> int:
@@ -63,6 +66,37 @@ class Circuit:
 
     def mux_naive(self, a, b, c):          # gates.rs:189-199
         return self.or_(self.and_(a, b), self.and_(self.not_(a), c))
+
+    def mux(self, a, b, c):
+        """a ? b : c as the sound fused multiplexer (what gates.rs:157-183 intends): AND(a, b) and
+        AND(!a, c) are added at level 1 and key-switched once -- one level, 2 blind rotations."""
+        return self._add("MUX", a, b, c)
+
+    # src/circuits.rs:3-6 (compare_bit); the comparator built from it
+    def compare_bit(self, a, b, lsb_carry):
+        """carry out of one comparator cell: a == b ? lsb_carry : a."""
+        return self.mux(self.xnor_true(a, b), lsb_carry, a)
+
+    def xnor_true(self, a, b):
+        """logical XNOR.  Gates::xnor decrypts to XOR in the reference (gates.rs:86-90, pinned by its own
+        test, :575-579), so equality is NOT(xor)."""
+        return self.not_(self.xor(a, b))
+
+    def greater_than(self, a: Sequence[int], b: Sequence[int]) -> int:
+        """a > b for little-endian bit vectors: fold compare_bit from the least significant bit."""
+        assert len(a) == len(b)
+        carry = self.constant(False)
+        for x, y in zip(a, b):
+            carry = self.compare_bit(x, y, carry)
+        return carry
+
+    def equals(self, a: Sequence[int], b: Sequence[int]) -> int:
+        """a == b: AND-tree over the per-bit equalities (src/circuits.rs leaves `equals` empty)."""
+        assert len(a) == len(b)
+        eq = [self.xnor_true(x, y) for x, y in zip(a, b)]
+        while len(eq) > 1:
+            eq = [self.and_(eq[i], eq[i + 1]) if i + 1 < len(eq) else eq[i] for i in range(0, len(eq), 2)]
+        return eq[0]
 
     # examples/add_two_numbers.rs:11-29
     def full_adder(self, a, b, c) -> Tuple[int, int]:
@@ -98,6 +132,9 @@ class Circuit:
             elif g.op in ("NOT", "COPY"):
                 depth[w] = depth[g.a]
                 free.setdefault(depth[w], []).append(w)
+            elif g.op == "MUX":
+                depth[w] = 1 + max(depth[g.a], depth[g.b], depth[g.c])
+                lv.setdefault(depth[w], []).append(w)
             else:
                 depth[w] = 1 + max(depth[g.a], depth[g.b])
                 lv.setdefault(depth[w], []).append(w)
@@ -107,58 +144,48 @@ class Circuit:
         return self.schedule()[0]
 
     def bootstrapped_gate_count(self) -> int:
-        return sum(len(l) for l in self.levels())
+        """blind rotations per input set (a fused MUX costs two)"""
+        return sum(2 if self.gates[w].op == "MUX" else 1 for l in self.levels() for w in l)
 
 
 def evaluate(circuit: Circuit, engine: CudaBootstrap, inputs: np.ndarray) -> np.ndarray:
     """Evaluate `circuit` on `inputs` u32[num_inputs][batch][n+1] (one ciphertext per input wire
-    and batch element).  Returns u32[num_outputs][batch][n+1].  Level by level, device-resident."""
-    import torch
-
+    and batch element).  Returns u32[num_outputs][batch][n+1].  The circuit is handed to the library
+    (tfhe_circuit_*), which levelises it and runs every level as one device batch with the wires
+    resident in HBM; `engine.last_kernel_ms()` afterwards holds the summed kernel times."""
+    L = _load()
     n1 = engine.params.n + 1
     inputs = np.ascontiguousarray(inputs, dtype=np.uint32)
     if inputs.ndim != 3 or inputs.shape[0] != len(circuit.inputs) or inputs.shape[2] != n1:
         raise ValueError("inputs must be [num_inputs][batch][n+1]")
     batch = inputs.shape[1]
-    dev = torch.device("cuda", engine.device)
-    # one explicit stream carries both torch's gather/scatter and the engine's kernels
-    # (handle 0 -- the legacy default stream -- would mean "engine's own stream" to the ABI)
-    stream = torch.cuda.Stream(device=dev)
-    engine.set_stream(stream.cuda_stream)
+    h = C.c_void_p()
+    _check(L.tfhe_circuit_create(engine._h, C.byref(h)))
     try:
-        with torch.cuda.stream(stream):
-            nw = len(circuit.gates)
-            wires = torch.zeros((nw, batch, n1), dtype=torch.int32, device=dev)
-            wires[torch.tensor(circuit.inputs, device=dev)] = torch.from_numpy(inputs.view(np.int32)).to(dev)
-            mu = f64_to_torus(0.125)
-            levels, free = circuit.schedule()
-
-            def run_free(d: int) -> None:
-                # linear gates need no bootstrap (gates.rs:202-218); recording order within a depth
-                for w in free.get(d, []):
-                    g = circuit.gates[w]
-                    if g.op == "NOT":
-                        wires[w] = -wires[g.a]
-                    elif g.op == "COPY":
-                        wires[w] = wires[g.a]
-                    else:
-                        v = mu if g.op == "CONST1" else (1 - mu) & 0xFFFFFFFF
-                        wires[w, :, -1] = v - (1 << 32) if v >= (1 << 31) else v
-
-            run_free(0)
-            for d, level in enumerate(levels, start=1):
-                a_idx = torch.tensor([circuit.gates[w].a for w in level], device=dev)
-                b_idx = torch.tensor([circuit.gates[w].b for w in level], device=dev)
-                pairs = torch.stack([wires[a_idx], wires[b_idx]], dim=2).reshape(-1, 2, n1).contiguous()
-                ops = torch.tensor([_CODE[circuit.gates[w].op] for w in level], dtype=torch.uint8,
-                                   device=dev).repeat_interleave(batch).contiguous()
-                out = torch.empty((len(level) * batch, n1), dtype=torch.int32, device=dev)
-                engine.batch_gate_dev(0, pairs.data_ptr(), out.data_ptr(), len(level) * batch,
-                                      d_ops=ops.data_ptr())
-                wires[torch.tensor(level, device=dev)] = out.view(len(level), batch, n1)
-                run_free(d)
-            res = wires[torch.tensor(circuit.outputs, device=dev)].cpu().numpy().view(np.uint32)
-            stream.synchronize()
-            return res
+        wire = {}
+        out = C.c_uint32()
+        for wid, g in enumerate(circuit.gates):
+            if g.op == "INPUT":
+                _check(L.tfhe_circuit_input(h, C.byref(out)))
+            elif g.op in ("CONST0", "CONST1"):
+                _check(L.tfhe_circuit_constant(h, int(g.op == "CONST1"), C.byref(out)))
+            elif g.op == "NOT":
+                _check(L.tfhe_circuit_not(h, wire[g.a], C.byref(out)))
+            elif g.op == "COPY":
+                wire[wid] = wire[g.a]
+                continue
+            elif g.op == "MUX":
+                _check(L.tfhe_circuit_mux(h, wire[g.a], wire[g.b], wire[g.c], C.byref(out)))
+            else:
+                _check(L.tfhe_circuit_gate(h, _CODE[g.op], wire[g.a], wire[g.b], C.byref(out)))
+            wire[wid] = out.value
+        for w in circuit.outputs:
+            _check(L.tfhe_circuit_output(h, wire[w]))
+        res = np.empty((len(circuit.outputs), batch, n1), dtype=np.uint32)
+        _check(L.tfhe_circuit_run(h, inputs.ctypes.data_as(C.c_void_p), res.ctypes.data_as(C.c_void_p), batch))
+        lv, pbs, ks = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        _check(L.tfhe_circuit_stats(h, C.byref(lv), C.byref(pbs), C.byref(ks)))
+        circuit.last_stats = {"levels": lv.value, "bootstraps": pbs.value, "key_switches": ks.value}
+        return res
     finally:
-        engine.set_stream(0)
+        L.tfhe_circuit_destroy(h)

@@ -18,9 +18,11 @@
 #include <stdlib.h>
 
 #include "br_core.cuh"
+#include "br_ptx.cuh"
 #include "kernels.h"
 
 using namespace br;
+using namespace brp;
 
 #ifndef BR_PRODUCER_SLEEP_NS
 #define BR_PRODUCER_SLEEP_NS 256
@@ -31,68 +33,10 @@ using namespace br;
 
 namespace {
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// producer-side wait: back off between polls so the spin does not steal issue slots
-// from the consumer warps sharing its SM sub-partition
+__device__ __forceinline__ void group_sync(int g) { named_sync<64>(g + 1); }
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) __nanosleep(BR_PRODUCER_SLEEP_NS);
+  brp::mbar_wait_backoff(bar, parity, BR_PRODUCER_SLEEP_NS);
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-// 1-D TMA bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes,
-                                            uint64_t *bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void group_sync(int g) {
-  asm volatile("bar.sync %0, 64;" ::"r"(g + 1) : "memory");
-}
-
-// gates.rs:54-150: out = ca*a + cb*b, b-word += off
-__constant__ int32_t c_gate_ca[TFHE_GATE_COUNT] = {-1, 1, 1, 1, 1, -1, -1, 1, -1, 1};
-__constant__ int32_t c_gate_cb[TFHE_GATE_COUNT] = {-1, 1, 1, 2, -2, -1, 1, -1, 1, -1};
-__constant__ uint32_t c_gate_off[TFHE_GATE_COUNT] = {0x20000000u, 0xE0000000u, 0x20000000u,
-                                                     0x40000000u, 0xC0000000u, 0xE0000000u,
-                                                     0xE0000000u, 0xE0000000u, 0x20000000u,
-                                                     0x20000000u};
 
 constexpr int kStageBytes = kChunkCplx * 16;  // 16 KB: one BSK row
 
@@ -156,283 +100,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
-// park / restore one output's 8 complex accumulators (32 words) at TMEM column `col`
-__device__ __forceinline__ void park8(uint32_t taddr, const cplx (&a)[8]) {
-  uint32_t r[32];
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    r[4 * i + 0] = (uint32_t)__double2loint(a[i].x); r[4 * i + 1] = (uint32_t)__double2hiint(a[i].x);
-    r[4 * i + 2] = (uint32_t)__double2loint(a[i].y); r[4 * i + 3] = (uint32_t)__double2hiint(a[i].y);
-  }
-  tmem_st32(taddr, r);
-}
-__device__ __forceinline__ void unpark8(uint32_t taddr, cplx (&a)[8]) {
-  uint32_t r[32];
-  tmem_ld32(taddr, r);
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    a[i].x = __hiloint2double((int)r[4 * i + 1], (int)r[4 * i + 0]);
-    a[i].y = __hiloint2double((int)r[4 * i + 3], (int)r[4 * i + 2]);
-  }
-}
-
-template <int L, int NBUF> struct Cfg {
-  static constexpr int kAccBytes = 2 * kN * 4;
-  static constexpr int kExchBytes = NBUF * kExchStride * 16;
-  static constexpr int kAbarBytes = 2432;  // u16[n], n <= 1216
-  static constexpr int kGroupBytes = kAccBytes + kExchBytes + kAbarBytes;
-};
-
-// Kernel variants (same per-thread code, different residency):
-//   V1: G=4 groups, 3 exchange buffers, twiddles in registers   (consumers 232 regs)
-//   V2: G=6 groups, 2 exchange buffers (digits in sub-rounds of <=2), pass-A twiddles in
-//       TMEM, pass-B twiddles rebuilt from three base values     (consumers 160 regs)
-//   MAGIC: int<->double conversions of the exact regime as 2^52-biased bit patterns + one DADD
-//       (FP64 pipe) instead of I2F/F2I (quarter-rate conversion pipe).
-template <int L, int BGBIT, int G, int STAGES, int NBUF, bool TMEM_TW, int REGS_CONS, int REGS_PROD,
-          bool PARK = false, bool MAGIC = false>
-__global__ void __launch_bounds__(((2 * G + 3) / 4) * 128 + 128, 1) blind_rotate_kernel(const BrArgs args) {
-  static_assert(!MAGIC || (L == 3 && BGBIT == 6), "MAGIC conversions need the exact regime");
-  using C = Cfg<L, NBUF>;
-  constexpr int PW = ((2 * G + 3) / 4) * 4;  // first producer warp: its own warpgroup
-  constexpr int L2 = 2 * L;
-  constexpr bool EXACT = (L == 3 && BGBIT == 6);
-  static_assert(NBUF >= 2 && (L <= NBUF || (L == 3 && NBUF == 2)), "unsupported buffer plan");
-  constexpr int ND0 = L <= NBUF ? L : 2;   // digits in the first sub-round
-  constexpr int ND1 = L - ND0;             // and in the second (0 or 1)
-  extern __shared__ __align__(128) uint8_t smem[];
-  cplx *ring = reinterpret_cast<cplx *>(smem);
-  uint8_t *groups = smem + STAGES * kStageBytes;
-  uint64_t *full = reinterpret_cast<uint64_t *>(groups + G * C::kGroupBytes);
-  uint64_t *empty = full + STAGES;
-  uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(empty + STAGES);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t n = args.n;
-  const uint32_t grid = gridDim.x;
-  const uint32_t per_round = grid * G;
-  const uint32_t rounds = (uint32_t)((args.count + per_round - 1) / per_round);
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; s++) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 2 * G);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (TMEM_TW && warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
-        smem_u32(tmem_base_s)));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  if (TMEM_TW) asm volatile("tcgen05.fence::before_thread_sync;");
-  __syncthreads();
-  if (TMEM_TW) asm volatile("tcgen05.fence::after_thread_sync;");
-
-  // Register budget: the SM sub-partition hosting the producer warpgroup also hosts
-  // consumer warps, so the launch is compiled at 65536/blockDim registers/thread and
-  // rebalanced here (SASS: USETMAXREG).
-  if (warp >= PW) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PROD));
-    // ===== producer: stream BSK rows (i, r) for every round =====
-    if (warp == PW && lane == 0) {
-      const uint8_t *src0 = reinterpret_cast<const uint8_t *>(args.bsk);
-      uint32_t stage = 0, parity = 0;
-      const uint32_t rows = n * L2;
-      for (uint32_t rd = 0; rd < rounds; rd++) {
-        for (uint32_t row = 0; row < rows; row++) {
-          mbar_wait_backoff(&empty[stage], parity ^ 1);
-          mbar_arrive_expect_tx(&full[stage], kStageBytes);
-          tma_load_1d(reinterpret_cast<uint8_t *>(ring) + stage * kStageBytes,
-                      src0 + (size_t)row * kStageBytes, kStageBytes, &full[stage]);
-          if (++stage == STAGES) { stage = 0; parity ^= 1; }
-        }
-      }
-    }
-    return;
-  }
-
-  // ===== consumers: group g owns one ciphertext per round =====
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_CONS));
-  if (warp >= 2 * G) return;  // padding warps of a partially filled consumer warpgroup (odd G)
-  const int g = warp >> 1;
-  const int tid = threadIdx.x & 63;
-  uint8_t *gbase = groups + g * C::kGroupBytes;
-  uint32_t *acc = reinterpret_cast<uint32_t *>(gbase);
-  cplx *exch = reinterpret_cast<cplx *>(gbase + C::kAccBytes);
-  uint16_t *abar_s = reinterpret_cast<uint16_t *>(gbase + C::kAccBytes + C::kExchBytes);
-
-  // twiddles: V1 keeps both sets in registers; V2 parks ta in TMEM and keeps 3 tb bases
-  cplx ta_reg[TMEM_TW ? 1 : 8], tb_reg[TMEM_TW ? 1 : 8];
-  cplx tb1, tb2, tb4;
-  uint32_t taddr = 0;
-  {
-    const cplx *twb = args.tw_b + (tid & 7) * 8;
-    tb1 = twb[1]; tb2 = twb[2]; tb4 = twb[4];
-    if constexpr (TMEM_TW) {
-      cplx ta[8];
-#pragma unroll
-      for (int k = 0; k < 8; k++) ta[k] = args.tw_a[tid * 8 + k];
-      taddr = *tmem_base_s + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * 96u;
-      tmem_st_ta(taddr, ta);
-    } else {
-#pragma unroll
-      for (int k = 0; k < 8; k++) { ta_reg[k] = args.tw_a[tid * 8 + k]; tb_reg[k] = twb[k]; }
-    }
-  }
-#define BR_GET_TA(dst)                                   \
-  cplx dst[8];                                           \
-  if constexpr (TMEM_TW) tmem_ld_ta(taddr, dst);         \
-  else { _Pragma("unroll") for (int k_ = 0; k_ < 8; k_++) dst[k_] = ta_reg[k_]; }
-#define BR_GET_TB(dst)                                   \
-  cplx dst[8];                                           \
-  if constexpr (TMEM_TW) expand_tb(tb1, tb2, tb4, dst);  \
-  else { _Pragma("unroll") for (int k_ = 0; k_ < 8; k_++) dst[k_] = tb_reg[k_]; }
-#define BR_MAC_DIGITS(ND)                                                                   \
-  _Pragma("unroll") for (int d = 0; d < (ND); d++) {                                        \
-    mbar_wait(&full[stage], parity);                                                        \
-    fwd_pass_c_mac(tid, exch + d * kExchStride, ring + stage * kChunkCplx, racc);           \
-    __syncwarp();                                                                           \
-    if (lane == 0) mbar_arrive(&empty[stage]);                                              \
-    if (++stage == STAGES) { stage = 0; parity ^= 1; }                                      \
-  }
-
-  const uint32_t w = n + 1;
-  uint32_t stage = 0, parity = 0;
-
-  for (uint32_t rd = 0; rd < rounds; rd++) {
-    const size_t ct = ((size_t)rd * G + g) * grid + blockIdx.x;
-    const bool active = ct < args.count;
-
-    if (active) {
-      // ---- K0: linear pre-combination + modulus switch (trgsw.rs:202-203, 210-211)
-      uint32_t ca = 1, cb = 0, off = 0;
-      const uint32_t *A, *B;
-      if (args.op >= 0 || args.ops) {
-        int op = args.ops ? (int)args.ops[ct] : args.op;
-        ca = (uint32_t)c_gate_ca[op]; cb = (uint32_t)c_gate_cb[op]; off = c_gate_off[op];
-        A = args.in + ct * 2 * w;
-        B = A + w;
-      } else {
-        A = args.in + ct * w;
-        B = A;
-      }
-      for (uint32_t i = tid; i < n; i += 64) {
-        uint32_t v = ca * A[i] + cb * B[i];
-        abar_s[i] = (uint16_t)((uint32_t)(v + (1u << 20)) >> 21);
-      }
-      uint32_t bw = ca * A[n] + cb * B[n] + off;
-      uint32_t b_tilda = (uint32_t)(2 * kN - (((uint64_t)bw + (1u << 20)) >> 21));
-      const int tvi = args.tv_index ? args.tv_index[ct] : args.tv_default;
-      const uint32_t *tv = args.tv + (size_t)tvi * 2 * kN;
-      for (int x = tid; x < 2 * kN; x += 64)
-        acc[x] = rot_coeff(tv + (x & ~(kN - 1)), x & (kN - 1), b_tilda);
-    }
-    group_sync(g);
-
-    for (uint32_t i = 0; i < n; i++) {
-      if (active) {
-        cplx racc[2][8];
-        const uint32_t abar = abar_s[i];
-#pragma unroll
-        for (int o = 0; o < 2; o++)
-#pragma unroll
-          for (int k = 0; k < 8; k++) racc[o][k] = mk(0.0, 0.0);
-#pragma unroll 1
-        for (int p = 0; p < 2; p++) {
-          uint32_t t_re[8], t_im[8];
-          load_t(tid, acc + p * kN, abar, args.offset, t_re, t_im);
-          {
-            BR_GET_TA(ta)
-            fwd_pass_a<BGBIT, 0, ND0, MAGIC>(tid, t_re, t_im, ta, exch);
-          }
-          group_sync(g);
-          {
-            BR_GET_TB(tb)
-            fwd_pass_b<ND0>(tid, tb, exch);
-          }
-          group_sync(g);
-          if (PARK && p == 1) {   // accumulators were parked in TMEM during poly b's passes A/B
-            unpark8(taddr + 32, racc[0]);
-            unpark8(taddr + 64, racc[1]);
-          }
-          BR_MAC_DIGITS(ND0)
-          if (PARK && p == 0 && ND1 == 0) {
-            park8(taddr + 32, racc[0]);
-            park8(taddr + 64, racc[1]);
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-          }
-          group_sync(g);
-          if constexpr (ND1 > 0) {
-            {
-              BR_GET_TA(ta)
-              fwd_pass_a<BGBIT, ND0, ND1, MAGIC>(tid, t_re, t_im, ta, exch);
-            }
-            group_sync(g);
-            {
-              BR_GET_TB(tb)
-              fwd_pass_b<ND1>(tid, tb, exch);
-            }
-            group_sync(g);
-            BR_MAC_DIGITS(ND1)
-            group_sync(g);
-          }
-        }
-        {
-          BR_GET_TB(tb)
-          inv_pass_c(tid, tb, racc, exch);
-        }
-        group_sync(g);
-        inv_pass_b(tid, exch);
-        group_sync(g);
-        {
-          BR_GET_TA(ta)
-          inv_pass_a<EXACT, MAGIC>(tid, ta, exch, acc);
-        }
-        group_sync(g);
-      } else {
-        // idle group: keep the ring's phase accounting in lock step
-        for (int c = 0; c < L2; c++) {
-          mbar_wait(&full[stage], parity);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty[stage]);
-          if (++stage == STAGES) { stage = 0; parity ^= 1; }
-        }
-      }
-    }
-
-    if (active) {
-      // ---- epilogue: TRLWE, or fused sample extraction (trlwe.rs:106-136)
-      if (args.out_mode == BR_OUT_TRLWE) {
-        uint32_t *o = args.out + ct * 2 * kN;
-        for (int x = tid; x < 2 * kN; x += 64) o[x] = acc[x];
-      } else {
-        const uint32_t m = args.out_mode == BR_OUT_EXTRACT ? (uint32_t)kN : n;
-        uint32_t *o = args.out + ct * (m + 1);
-        for (uint32_t x = tid; x <= m; x += 64) {
-          uint32_t v;
-          if (x == 0) v = acc[0];
-          else if (x == m) v = acc[kN];
-          else v = ~acc[m - x];
-          o[x] = v;
-        }
-      }
-    }
-    group_sync(g);
-  }
-#undef BR_GET_TA
-#undef BR_GET_TB
-#undef BR_MAC_DIGITS
-  if constexpr (TMEM_TW) {
-    asm volatile("bar.sync 15, %0;" ::"n"(G * 64) : "memory");  // all consumers done with TMEM
-    if (warp == 0)
-      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(*tmem_base_s));
-  }
-}
-
-// completion of every outstanding tcgen05.ld of this thread; the loaded registers are threaded
-// through as in/out operands so no use can be scheduled above the wait
 __device__ __forceinline__ void tmem_wait_ld16(uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
                : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
@@ -636,35 +303,11 @@ __global__ void __launch_bounds__(384, 1) blind_rotate_kernel_x(const BrArgs arg
     for (int sl = 0; sl < 8; sl++) t[sl] = args.tw_b[c_k1 * 8 + (sl ^ (4 * l4))];   // w64^(j0 k1), j0 = p ^ 4 l4
     tmem_park8(t_tbi, t);
   }
-  const uint32_t w = n + 1;
   uint32_t stage = 0, parity = 0;
   for (uint32_t rd = 0; rd < rounds; rd++) {
     const size_t ct = ((size_t)rd * G + g) * grid + blockIdx.x;
     const bool active = ct < args.count;
-    if (active) {
-      // ---- K0: linear pre-combination + modulus switch (trgsw.rs:202-203, 210-211)
-      uint32_t ca = 1, cb = 0, off = 0;
-      const uint32_t *A, *B;
-      if (args.op >= 0 || args.ops) {
-        int op = args.ops ? (int)args.ops[ct] : args.op;
-        ca = (uint32_t)c_gate_ca[op]; cb = (uint32_t)c_gate_cb[op]; off = c_gate_off[op];
-        A = args.in + ct * 2 * w;
-        B = A + w;
-      } else {
-        A = args.in + ct * w;
-        B = A;
-      }
-      for (uint32_t i = tid; i < n; i += 64) {
-        uint32_t v = ca * A[i] + cb * B[i];
-        abar_s[i] = (uint16_t)((uint32_t)(v + (1u << 20)) >> 21);
-      }
-      uint32_t bw = ca * A[n] + cb * B[n] + off;
-      uint32_t b_tilda = (uint32_t)(2 * kN - (((uint64_t)bw + (1u << 20)) >> 21));
-      const int tvi = args.tv_index ? args.tv_index[ct] : args.tv_default;
-      const uint32_t *tv = args.tv + (size_t)tvi * 2 * kN;
-      for (int x = tid; x < 2 * kN; x += 64)
-        acc[x] = rot_coeff(tv + (x & ~(kN - 1)), x & (kN - 1), b_tilda);
-    }
+    if (active) prologue<64>(args, ct, tid, abar_s, acc);   // K0 (br_ptx.cuh)
     group_sync(g);
     for (uint32_t i = 0; i < n; i++) {
       if (active) {
@@ -744,23 +387,7 @@ __global__ void __launch_bounds__(384, 1) blind_rotate_kernel_x(const BrArgs arg
         }
       }
     }
-    if (active) {
-      // ---- epilogue: TRLWE, or fused sample extraction (trlwe.rs:106-136)
-      if (args.out_mode == BR_OUT_TRLWE) {
-        uint32_t *o = args.out + ct * 2 * kN;
-        for (int x = tid; x < 2 * kN; x += 64) o[x] = acc[x];
-      } else {
-        const uint32_t m = args.out_mode == BR_OUT_EXTRACT ? (uint32_t)kN : n;
-        uint32_t *o = args.out + ct * (m + 1);
-        for (uint32_t x = tid; x <= m; x += 64) {
-          uint32_t v;
-          if (x == 0) v = acc[0];
-          else if (x == m) v = acc[kN];
-          else v = ~acc[m - x];
-          o[x] = v;
-        }
-      }
-    }
+    if (active) epilogue<64>(args, ct, tid, acc);
     group_sync(g);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -780,228 +407,6 @@ cudaError_t launch_x(const BrArgs &args, int num_sms, cudaStream_t stream) {
   int grid = (int)(args.count < (size_t)num_sms ? args.count : (size_t)num_sms);
   if (grid < 1) grid = 1;
   kern<<<grid, 384, smem, stream>>>(args);
-  return cudaGetLastError();
-}
-
-// ---- V4: six groups per SM ------------------------------------------------------------
-// The 2l digit polynomials of a step (rows 0..2l-1 of BSK[i]) go through the two exchange
-// buffers in PAIRS (a0,a1 | a2,b0 | b1,b2 at l=3), so a step has 3l+3 group barriers.  Between
-// MAC phases the 2x8 complex accumulators are parked in TMEM next to the pass-A twiddles, so
-// passes A and B run with ~100 live registers and the whole kernel fits 160 registers/thread
-// without spills -- which is what lets 12 consumer warps (3 per sub-partition) stay resident.
-template <int L, int BGBIT>
-__global__ void __launch_bounds__(6 * 64 + 128, 1) blind_rotate_kernel_v4(const BrArgs args) {
-  constexpr int G = 6, STAGES = 3, NBUF = 2;
-  using C = Cfg<L, NBUF>;
-  constexpr int L2 = 2 * L;
-  constexpr bool EXACT = (L == 3 && BGBIT == 6);
-  extern __shared__ __align__(128) uint8_t smem[];
-  cplx *ring = reinterpret_cast<cplx *>(smem);
-  uint8_t *groups = smem + STAGES * kStageBytes;
-  uint64_t *full = reinterpret_cast<uint64_t *>(groups + G * C::kGroupBytes);
-  uint64_t *empty = full + STAGES;
-  uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(empty + STAGES);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t n = args.n;
-  const uint32_t grid = gridDim.x;
-  const uint32_t per_round = grid * G;
-  const uint32_t rounds = (uint32_t)((args.count + per_round - 1) / per_round);
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; s++) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 2 * G);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
-        smem_u32(tmem_base_s)));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;");
-
-  if (warp >= 2 * G) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-    if (warp == 2 * G && lane == 0) {
-      const uint8_t *src0 = reinterpret_cast<const uint8_t *>(args.bsk);
-      uint32_t stage = 0, parity = 0;
-      const uint32_t rows = n * L2;
-      for (uint32_t rd = 0; rd < rounds; rd++)
-        for (uint32_t row = 0; row < rows; row++) {
-          mbar_wait_backoff(&empty[stage], parity ^ 1);
-          mbar_arrive_expect_tx(&full[stage], kStageBytes);
-          tma_load_1d(reinterpret_cast<uint8_t *>(ring) + stage * kStageBytes,
-                      src0 + (size_t)row * kStageBytes, kStageBytes, &full[stage]);
-          if (++stage == STAGES) { stage = 0; parity ^= 1; }
-        }
-    }
-    return;
-  }
-
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
-  const int g = warp >> 1;
-  const int tid = threadIdx.x & 63;
-  uint8_t *gbase = groups + g * C::kGroupBytes;
-  uint32_t *acc = reinterpret_cast<uint32_t *>(gbase);
-  cplx *exch = reinterpret_cast<cplx *>(gbase + C::kAccBytes);
-  uint16_t *abar_s = reinterpret_cast<uint16_t *>(gbase + C::kAccBytes + C::kExchBytes);
-
-  // TMEM columns of this thread: [0,32) pass-A twiddles, [32,64) racc[0], [64,96) racc[1]
-  const uint32_t taddr = *tmem_base_s + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * 96u;
-  cplx tb1, tb2, tb4;
-  {
-    const cplx *twb = args.tw_b + (tid & 7) * 8;
-    tb1 = twb[1]; tb2 = twb[2]; tb4 = twb[4];
-    cplx ta[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) ta[k] = args.tw_a[tid * 8 + k];
-    tmem_st_ta(taddr, ta);
-  }
-
-  const uint32_t w = n + 1;
-  uint32_t stage = 0, parity = 0;
-
-  for (uint32_t rd = 0; rd < rounds; rd++) {
-    const size_t ct = ((size_t)rd * G + g) * grid + blockIdx.x;
-    const bool active = ct < args.count;
-
-    if (active) {
-      uint32_t ca = 1, cb = 0, off = 0;
-      const uint32_t *A, *B;
-      if (args.op >= 0 || args.ops) {
-        int op = args.ops ? (int)args.ops[ct] : args.op;
-        ca = (uint32_t)c_gate_ca[op]; cb = (uint32_t)c_gate_cb[op]; off = c_gate_off[op];
-        A = args.in + ct * 2 * w;
-        B = A + w;
-      } else {
-        A = args.in + ct * w;
-        B = A;
-      }
-      for (uint32_t i = tid; i < n; i += 64) {
-        uint32_t v = ca * A[i] + cb * B[i];
-        abar_s[i] = (uint16_t)((uint32_t)(v + (1u << 20)) >> 21);
-      }
-      uint32_t bw = ca * A[n] + cb * B[n] + off;
-      uint32_t b_tilda = (uint32_t)(2 * kN - (((uint64_t)bw + (1u << 20)) >> 21));
-      const int tvi = args.tv_index ? args.tv_index[ct] : args.tv_default;
-      const uint32_t *tv = args.tv + (size_t)tvi * 2 * kN;
-      for (int x = tid; x < 2 * kN; x += 64)
-        acc[x] = rot_coeff(tv + (x & ~(kN - 1)), x & (kN - 1), b_tilda);
-    }
-    group_sync(g);
-
-    for (uint32_t i = 0; i < n; i++) {
-      if (active) {
-        const uint32_t abar = abar_s[i];
-        // sub-round s: rows 2s, 2s+1 of BSK[i]; row r = digit (r % L) of polynomial (r / L).
-        // The loop stays rolled (one copy of the passes in the instruction cache).
-        cplx racc[2][8];
-#pragma unroll 1
-        for (int s = 0; s < L; s++) {
-          {
-            cplx ta[8];
-            tmem_ld_ta(taddr, ta);
-            uint32_t t_re[8], t_im[8];
-            const int p0 = (2 * s) / L, p1 = (2 * s + 1) / L;
-            load_t(tid, acc + p0 * kN, abar, args.offset, t_re, t_im);
-            fwd_pass_a_rt<BGBIT>(tid, t_re, t_im, ta, exch, (2 * s) % L);
-            if (p1 != p0) load_t(tid, acc + p1 * kN, abar, args.offset, t_re, t_im);
-            fwd_pass_a_rt<BGBIT>(tid, t_re, t_im, ta, exch + kExchStride, (2 * s + 1) % L);
-          }
-          group_sync(g);
-          {
-            cplx tb[8];
-            expand_tb(tb1, tb2, tb4, tb);
-            fwd_pass_b<2>(tid, tb, exch);
-          }
-          group_sync(g);
-          if (s == 0) {
-#pragma unroll
-            for (int o = 0; o < 2; o++)
-#pragma unroll
-              for (int k = 0; k < 8; k++) racc[o][k] = mk(0.0, 0.0);
-          } else {
-            unpark8(taddr + 32, racc[0]);
-            unpark8(taddr + 64, racc[1]);
-          }
-#pragma unroll
-          for (int q = 0; q < 2; q++) {
-            mbar_wait(&full[stage], parity);
-            fwd_pass_c_mac(tid, exch + q * kExchStride, ring + stage * kChunkCplx, racc);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[stage]);
-            if (++stage == STAGES) { stage = 0; parity ^= 1; }
-          }
-          if (s < L - 1) {
-            park8(taddr + 32, racc[0]);
-            park8(taddr + 64, racc[1]);
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-          }
-          group_sync(g);  // everyone is done reading exch
-        }
-        {
-          cplx tb[8];
-          expand_tb(tb1, tb2, tb4, tb);
-          inv_pass_c(tid, tb, racc, exch);
-        }
-        group_sync(g);
-        inv_pass_b(tid, exch);
-        group_sync(g);
-        {
-          cplx ta[8];
-          tmem_ld_ta(taddr, ta);
-          inv_pass_a<EXACT>(tid, ta, exch, acc);
-        }
-        group_sync(g);
-      } else {
-        for (int c = 0; c < L2; c++) {
-          mbar_wait(&full[stage], parity);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty[stage]);
-          if (++stage == STAGES) { stage = 0; parity ^= 1; }
-        }
-      }
-    }
-
-    if (active) {
-      if (args.out_mode == BR_OUT_TRLWE) {
-        uint32_t *o = args.out + ct * 2 * kN;
-        for (int x = tid; x < 2 * kN; x += 64) o[x] = acc[x];
-      } else {
-        const uint32_t m = args.out_mode == BR_OUT_EXTRACT ? (uint32_t)kN : n;
-        uint32_t *o = args.out + ct * (m + 1);
-        for (uint32_t x = tid; x <= m; x += 64) {
-          uint32_t v;
-          if (x == 0) v = acc[0];
-          else if (x == m) v = acc[kN];
-          else v = ~acc[m - x];
-          o[x] = v;
-        }
-      }
-    }
-    group_sync(g);
-  }
-  asm volatile("bar.sync 15, %0;" ::"n"(G * 64) : "memory");
-  if (warp == 0)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(*tmem_base_s));
-}
-
-template <int L, int BGBIT>
-cudaError_t launch_v4(const BrArgs &args, int num_sms, cudaStream_t stream) {
-  constexpr int G = 6, STAGES = 3;
-  auto kern = blind_rotate_kernel_v4<L, BGBIT>;
-  const int smem = STAGES * kStageBytes + G * Cfg<L, 2>::kGroupBytes + 2 * STAGES * 8 + 16;
-  {  // per device and cheap: set on every launch (engines may live on several GPUs)
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-  }
-  int grid = (int)(args.count < (size_t)num_sms ? args.count : (size_t)num_sms);
-  if (grid < 1) grid = 1;
-  kern<<<grid, G * 64 + 128, smem, stream>>>(args);
   return cudaGetLastError();
 }
 
@@ -1076,7 +481,6 @@ __global__ void __launch_bounds__(256, 1) blind_rotate_latency_kernel(const BrAr
   for (int k = 0; k < 8; k++) { ta[k] = args.tw_a[tid * 8 + k]; tb[k] = args.tw_b[(tid & 7) * 8 + k]; }
   auto cta_sync = [&]() { asm volatile("bar.sync 8, %0;" ::"n"(64 * NG) : "memory"); };
 
-  const uint32_t w = n + 1;
   uint32_t parity = 0;
   const int p0 = (2 * g) / L, p1 = (2 * g + 1) / L;       // polynomials of this group's two rows
   const int d0 = (2 * g) % L, d1 = (2 * g + 1) % L;       // and their digits
@@ -1084,29 +488,7 @@ __global__ void __launch_bounds__(256, 1) blind_rotate_latency_kernel(const BrAr
   for (uint32_t rd = 0; rd < rounds; rd++) {
     const size_t ct = (size_t)rd * grid + blockIdx.x;
     const bool active = ct < args.count;
-    if (active) {
-      uint32_t ca = 1, cb = 0, off = 0;
-      const uint32_t *A, *B;
-      if (args.op >= 0 || args.ops) {
-        int op = args.ops ? (int)args.ops[ct] : args.op;
-        ca = (uint32_t)c_gate_ca[op]; cb = (uint32_t)c_gate_cb[op]; off = c_gate_off[op];
-        A = args.in + ct * 2 * w;
-        B = A + w;
-      } else {
-        A = args.in + ct * w;
-        B = A;
-      }
-      for (uint32_t i = ctid; i < n; i += 64 * NG) {
-        uint32_t v = ca * A[i] + cb * B[i];
-        abar_s[i] = (uint16_t)((uint32_t)(v + (1u << 20)) >> 21);
-      }
-      uint32_t bw = ca * A[n] + cb * B[n] + off;
-      uint32_t b_tilda = (uint32_t)(2 * kN - (((uint64_t)bw + (1u << 20)) >> 21));
-      const int tvi = args.tv_index ? args.tv_index[ct] : args.tv_default;
-      const uint32_t *tv = args.tv + (size_t)tvi * 2 * kN;
-      for (int x = ctid; x < 2 * kN; x += 64 * NG)
-        acc[x] = rot_coeff(tv + (x & ~(kN - 1)), x & (kN - 1), b_tilda);
-    }
+    if (active) prologue<64 * NG>(args, ct, ctid, abar_s, acc);   // K0 (br_ptx.cuh)
     cta_sync();
 
     for (uint32_t i = 0; i < n; i++) {
@@ -1213,22 +595,7 @@ __global__ void __launch_bounds__(256, 1) blind_rotate_latency_kernel(const BrAr
       parity ^= 1;
     }
 
-    if (active) {
-      if (args.out_mode == BR_OUT_TRLWE) {
-        uint32_t *o = args.out + ct * 2 * kN;
-        for (int x = ctid; x < 2 * kN; x += 64 * NG) o[x] = acc[x];
-      } else {
-        const uint32_t m = args.out_mode == BR_OUT_EXTRACT ? (uint32_t)kN : n;
-        uint32_t *o = args.out + ct * (m + 1);
-        for (uint32_t x = ctid; x <= m; x += 64 * NG) {
-          uint32_t v;
-          if (x == 0) v = acc[0];
-          else if (x == m) v = acc[kN];
-          else v = ~acc[m - x];
-          o[x] = v;
-        }
-      }
-    }
+    if (active) epilogue<64 * NG>(args, ct, ctid, acc);
     cta_sync();
   }
 }
@@ -1247,28 +614,12 @@ cudaError_t launch_latency(const BrArgs &args, int num_sms, cudaStream_t stream)
   return cudaGetLastError();
 }
 
-template <int L, int BGBIT, int G, int STAGES, int NBUF, bool TMEM_TW, int RC, int RP, bool PARK = false,
-          bool MAGIC_REQ = false>
-cudaError_t launch_v(const BrArgs &args, int num_sms, cudaStream_t stream) {
-  constexpr bool MAGIC = MAGIC_REQ && L == 3 && BGBIT == 6;
-  auto kern = blind_rotate_kernel<L, BGBIT, G, STAGES, NBUF, TMEM_TW, RC, RP, PARK, MAGIC>;
-  const int smem = STAGES * kStageBytes + G * Cfg<L, NBUF>::kGroupBytes + 2 * STAGES * 8 + 16;
-  {  // per device and cheap: set on every launch (engines may live on several GPUs)
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-  }
-  int grid = (int)(args.count < (size_t)num_sms ? args.count : (size_t)num_sms);
-  if (grid < 1) grid = 1;
-  kern<<<grid, ((2 * G + 3) / 4) * 128 + 128, smem, stream>>>(args);
-  return cudaGetLastError();
-}
-
 int br_variant() {
   static int v = -1;
   if (v < 0) {
     const char *e = getenv("TFHE_BR_VARIANT");
     v = e ? atoi(e) : BR_DEFAULT_VARIANT;
-    if (v < 1 || v > 9) v = BR_DEFAULT_VARIANT;
+    if (v != 8 && v != 9) v = BR_DEFAULT_VARIANT;
   }
   return v;
 }
@@ -1319,18 +670,7 @@ cudaError_t launch_t(const BrArgs &args, int num_sms, cudaStream_t stream) {
     }
     return br_launch_s(L, BGBIT, br_slice(args, full, tail), num_sms, stream);
   }
-  // 7: variant 3 with the 2^52-bias conversions
-  if (br_variant() == 7) return launch_v<L, BGBIT, 4, 4, 3, true, 232, 40, false, true>(args, num_sms, stream);
-  if (br_variant() == 4) return launch_v4<L, BGBIT>(args, num_sms, stream);
-  if (br_variant() == 6)  // five groups per SM at 160 registers (3 exchange buffers, 2-stage ring)
-    return launch_v<L, BGBIT, 5, 2, 3, true, 160, 24, true>(args, num_sms, stream);
-  if (br_variant() == 5)  // variant 3 + MAC accumulators parked in TMEM across poly b's passes A/B
-    return launch_v<L, BGBIT, 4, 4, 3, true, 232, 40, true>(args, num_sms, stream);
-  if (br_variant() == 2)
-    return launch_v<L, BGBIT, 6, 3, 2, true, 160, 24>(args, num_sms, stream);
-  if (br_variant() == 3)  // V1 residency, but twiddles out of the register file (more ILP room)
-    return launch_v<L, BGBIT, 4, 4, 3, true, 232, 40>(args, num_sms, stream);
-  return launch_v<L, BGBIT, 4, 4, 3, false, 232, 40>(args, num_sms, stream);
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace

@@ -3,6 +3,7 @@
 // needs a CUDA device and fails loudly (TFHE_ERR_CUDA) without one.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -16,13 +17,14 @@
 
 #include <dlfcn.h>
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>
 #include <unistd.h>
 
 #include "kernels.h"
 #include "brs_core.cuh"
 
 #ifndef TFHE_KS_DEFAULT
-#define TFHE_KS_DEFAULT 0   // 0 = tcgen05 (umma), 1 = mma.sync, 2 = row walk
+#define TFHE_KS_DEFAULT 0   // 0 = tcgen05 (umma), 2 = row walk
 #endif
 
 namespace {
@@ -44,6 +46,14 @@ int fail(int code, const char *fmt, ...) {
       return fail(TFHE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
                   __FILE__, __LINE__);                                               \
   } while (0)
+
+// NVTX ranges (header-only NVTX v3; no-ops unless a profiler is attached): key upload / broadcast,
+// and per pipeline chunk H2D, blind rotation (K0+K3), key switch (K4), D2H -- the timeline rows an
+// nsys capture of a batch call shows.
+struct Nvtx {
+  explicit Nvtx(const char *name) { nvtxRangePushA(name); }
+  ~Nvtx() { nvtxRangePop(); }
+};
 
 constexpr int kMaxLut = 64;          // test-vector slots (slot 0 = cloud-key test vector,
                                      // slot kMaxLut-1 = scratch of the ephemeral bootstrap_func path)
@@ -93,7 +103,6 @@ struct tfhe_engine {
   cplx *tw_s = nullptr;   // per-thread constants of the 128-thread kernel
   uint8_t *kumma = nullptr;  // KSK as tcgen05 operand tiles (derived from the blob's KSK rows; gate sets)
   size_t blob_bytes = 0, off_ksk = 0, off_tv = 0;
-  uint32_t *kmma = nullptr;  // KSK as mma.sync B fragments (derived; only under TFHE_KS_VARIANT=mma, basebit 2)
   bool key_loaded = false;
   uint32_t decomp_offset = 0;
   uint32_t ksk_rows = 0, ksk_stride = 0;
@@ -154,14 +163,14 @@ void blob_layout(tfhe_engine *e) {
   e->blob_bytes = e->off_tv + (size_t)kMaxLut * 2 * TFHE_N * 4;
 }
 
-// K4 kernel selection: TFHE_KS_VARIANT = umma (default: tcgen05.mma, TMEM accumulators) | mma
-// (mma.sync, register accumulators) | rows (row-walk kernels; always used when basebit != 2).
-enum { KS_UMMA = 0, KS_MMA = 1, KS_ROWS = 2 };
+// K4 kernel selection: TFHE_KS_VARIANT = umma (default: tcgen05.mma, TMEM accumulators) | rows
+// (row-walk kernel; always used when the tcgen05 shape does not cover the set, e.g. basebit 7).
+enum { KS_UMMA = 0, KS_ROWS = 2 };
 int ks_variant() {
   static const int v = [] {
     const char *s = getenv("TFHE_KS_VARIANT");
     if (!s || !s[0]) return (int)TFHE_KS_DEFAULT;
-    return s[0] == 'r' ? (int)KS_ROWS : s[0] == 'm' ? (int)KS_MMA : (int)KS_UMMA;
+    return s[0] == 'r' ? (int)KS_ROWS : (int)KS_UMMA;
   }();
   return v;
 }
@@ -183,11 +192,6 @@ int finalize_key(tfhe_engine *e) {
   if (ks_variant() == KS_UMMA && ks_umma_supported(e->p.basebit, e->p.iks_t)) {
     if (!e->kumma) CU(cudaMalloc(reinterpret_cast<void **>(&e->kumma), ks_umma_key_bytes(e->p.n, e->p.iks_t, e->p.basebit)));
     CU(ksk_umma_relayout_launch(e->ksk(), e->ksk_stride, e->kumma, e->p.n, e->p.iks_t, e->p.basebit, e->stream));
-    e->launches++;
-  }
-  if (ks_variant() == KS_MMA && e->p.basebit == 2) {
-    if (!e->kmma) CU(cudaMalloc(reinterpret_cast<void **>(&e->kmma), ks_mma_words(e->p.n, e->p.iks_t) * 4));
-    CU(ksk_mma_relayout_launch(e->ksk(), e->ksk_stride, e->kmma, e->p.n, e->p.iks_t, e->stream));
     e->launches++;
   }
   CU(cudaStreamSynchronize(e->stream));
@@ -235,11 +239,6 @@ int key_switch(tfhe_engine *e, const uint32_t *d_ext, uint32_t *d_out, size_t co
     k.key = e->kumma; k.ext = d_ext; k.out = d_out;
     k.n = e->p.n; k.iks_t = e->p.iks_t; k.basebit = e->p.basebit; k.count = count;
     CU(ks_umma_launch(k, e->stream));
-  } else if (variant == KS_MMA && e->kmma) {
-    KsMmaArgs k{};
-    k.w = e->kmma; k.ext = d_ext; k.out = d_out;
-    k.n = e->p.n; k.iks_t = e->p.iks_t; k.nxg = ks_mma_nxg(e->p.n); k.count = count;
-    CU(ks_mma_launch(k, e->stream));
   } else {
     KsArgs k{};
     k.ksk = e->ksk(); k.ext = d_ext; k.out = d_out;
@@ -253,7 +252,7 @@ int key_switch(tfhe_engine *e, const uint32_t *d_ext, uint32_t *d_out, size_t co
 
 // One pass over <= kChunk ciphertexts already on the device.
 //   gate mode: op >= 0 or d_ops != NULL; plain mode: op < 0 and d_ops == NULL.
-//   out_kind: 0 key-switched LWE [n+1]; 1 extract_2 [n+1]; 2 TRLWE [2][N]
+//   out_kind: 0 key-switched LWE [n+1]; 1 extract_2 [n+1]; 2 TRLWE [2][N]; 3 extracted level-1 LWE [N+1]
 int run_device(tfhe_engine *e, tfhe_engine::Slot &sl, int op, const uint8_t *d_ops, int lut_id,
                const uint32_t *d_in, uint32_t *d_out, size_t count, int out_kind,
                const int32_t *d_lut_ids = nullptr) {
@@ -272,15 +271,19 @@ int run_device(tfhe_engine *e, tfhe_engine::Slot &sl, int op, const uint8_t *d_o
     a.out = static_cast<uint32_t *>(sl.ext.p);
     a.out_mode = BR_OUT_EXTRACT;
   } else {
-    a.out = d_out;
-    a.out_mode = out_kind == 1 ? BR_OUT_EXTRACT2 : BR_OUT_TRLWE;
+    a.out = d_out;   // 1: sample_extract_index_2 image [n+1]; 2: TRLWE; 3: level-1 sample [N+1], no key switch
+    a.out_mode = out_kind == 1 ? BR_OUT_EXTRACT2 : out_kind == 3 ? BR_OUT_EXTRACT : BR_OUT_TRLWE;
   }
   CU(cudaEventRecord(sl.br_start, e->stream));
-  int n_br = 0;
-  CU(br_launch(e->p.l, e->p.bgbit, a, e->num_sms, e->stream, &n_br));
-  e->launches += (uint64_t)n_br;
+  {
+    Nvtx r("tfhe:K0+K3 blind_rotate");
+    int n_br = 0;
+    CU(br_launch(e->p.l, e->p.bgbit, a, e->num_sms, e->stream, &n_br));
+    e->launches += (uint64_t)n_br;
+  }
   CU(cudaEventRecord(sl.br_end, e->stream));
   if (out_kind == 0) {
+    Nvtx r("tfhe:K4 key_switch");
     int rc = key_switch(e, static_cast<const uint32_t *>(sl.ext.p), d_out, count);
     if (rc != TFHE_OK) return rc;
   }
@@ -356,6 +359,8 @@ int run_host_locked(tfhe_engine *e, int op, const uint8_t *ops, int lut_id, cons
     if (rc != TFHE_OK) return rc;
     CU(sl.in.reserve(c * in_words * 4));
     CU(sl.out.reserve(c * out_words * 4));
+    Nvtx r_chunk("tfhe:chunk");
+    nvtxRangePushA("tfhe:H2D");
     const void *h_src = in + base * in_words;
     if (stage_in) {
       CU(sl.hin.reserve(chunk * in_words * 4));
@@ -376,10 +381,12 @@ int run_host_locked(tfhe_engine *e, int op, const uint8_t *ops, int lut_id, cons
       d_ids = static_cast<const int32_t *>(sl.idx.p);
     }
     CU(cudaEventRecord(sl.h2d_done, e->copy_in));
+    nvtxRangePop();
     CU(cudaStreamWaitEvent(e->stream, sl.h2d_done, 0));
     rc = run_device(e, sl, op, d_ops, lut_id, static_cast<const uint32_t *>(sl.in.p),
                     static_cast<uint32_t *>(sl.out.p), c, out_kind, d_ids);
     if (rc != TFHE_OK) return rc;
+    Nvtx r_d2h("tfhe:D2H");
     CU(cudaStreamWaitEvent(e->copy_out, sl.ks_end, 0));
     void *h_dst = out + base * out_words;
     if (stage_out) {
@@ -447,6 +454,7 @@ const NcclApi &nccl_api() {
 // vectors) to every peer over NVLink, then each peer derives its kernel-specific key orders.
 int broadcast_key(tfhe_engine *e, int n_lut_used) {
   if (e->peers.empty()) return TFHE_OK;
+  Nvtx r("tfhe:ncclBroadcast cloud key");
   const NcclApi &nc = nccl_api();
   ncclComm_t *comms = static_cast<ncclComm_t *>(e->nccl_comms);
   for (tfhe_engine *p : e->peers) {
@@ -676,7 +684,6 @@ void tfhe_engine_destroy(tfhe_engine *e) {
   if (e->bsk3) cudaFree(e->bsk3);
   if (e->tw_s) cudaFree(e->tw_s);
   if (e->kumma) cudaFree(e->kumma);
-  if (e->kmma) cudaFree(e->kmma);
   if (e->tw_a) cudaFree(e->tw_a);
   if (e->tw_b) cudaFree(e->tw_b);
   e->s_misc.release();
@@ -741,6 +748,7 @@ int tfhe_engine_load_cloud_key(tfhe_engine *e, uint32_t decomposition_offset,
                                const uint32_t *testvec_a, const uint32_t *testvec_b,
                                const uint32_t *ksk, const double *bsk) {
   if (!e || !testvec_a || !testvec_b || !ksk || !bsk) return fail(TFHE_ERR_INVALID, "null argument");
+  Nvtx r("tfhe:load_cloud_key (upload + re-layout + broadcast)");
   std::lock_guard<std::mutex> lock(e->mu);
   CU(cudaSetDevice(e->dev));
   int rc = ensure_blob(e);
@@ -1312,3 +1320,5 @@ int tfhe_engine_synchronize(tfhe_engine *e) {
 }
 
 }  // extern "C"
+
+#include "circuit.cuh"

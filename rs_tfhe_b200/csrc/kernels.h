@@ -55,22 +55,6 @@ struct KsArgs {
 cudaError_t ks_launch(const KsArgs &args, cudaStream_t stream);
 static inline uint32_t ks_stride(uint32_t n) { return (n + 1 + 3) & ~3u; }
 
-// K4 with mma.sync (keyswitch_mma.cu; TFHE_KS_VARIANT=mma), gate sets only (basebit == 2)
-struct KsMmaArgs {
-  const uint32_t *w;    // device order u32[N/8][t][8 ii][nxg][8 g8][4 planes]: bytes k=0..3 of plane p
-  const uint32_t *ext;  // [count][N+1]
-  uint32_t *out;        // [count][n+1]
-  uint32_t n, iks_t, nxg;
-  size_t count;
-};
-static inline uint32_t ks_mma_nxg(uint32_t n) { return ((n + 1 + 63) / 64) * 8; }  // groups of 8 words
-static inline size_t ks_mma_words(uint32_t n, uint32_t t) {
-  return (size_t)TFHE_N * t * ks_mma_nxg(n) * 8 * 4;
-}
-cudaError_t ks_mma_launch(const KsMmaArgs &args, cudaStream_t stream);
-cudaError_t ksk_mma_relayout_launch(const uint32_t *blob_rows, uint32_t stride, uint32_t *dst, uint32_t n,
-                                    uint32_t t, cudaStream_t stream);
-
 // K4 on the tcgen05 tensor cores (keyswitch_umma.cu): basebit 2..6 (gate sets, UINT1-6)
 struct KsUmmaArgs {
   const uint8_t *key;   // operand tiles, ku_layout.h: [n tile][stage][kstep 2][half 2][240 x 32 B canonical]

@@ -1,7 +1,7 @@
 // Addition to rs-tfhe's build.rs (the reference already uses `cc` for SPQLIOS, build.rs:7-24):
 // compile the CUDA sources for sm_100a and link the C ABI.  No multi-backend dispatch.
 fn build_cuda() {
-    let srcs = ["engine.cu", "blind_rotate.cu", "keyswitch.cu", "keyswitch_mma.cu", "keyswitch_umma.cu", "keygen.cu", "aux.cu"];
+    let srcs = ["engine.cu", "blind_rotate.cu", "blind_rotate_s.cu", "fft_seam.cu", "keyswitch.cu", "keyswitch_umma.cu", "keygen.cu", "aux.cu"];
     let dir = std::path::Path::new("rs_tfhe_b200/csrc");
     let out = std::path::PathBuf::from(std::env::var("OUT_DIR").unwrap());
     let lib = out.join("libtfhe_b200.so");

@@ -39,6 +39,8 @@ def test_library_is_sm100a_with_tma():
     sass = subprocess.run(["cuobjdump", "-sass", T.LIB_PATH], capture_output=True, text=True).stdout
     assert "UBLKCP" in sass      # TMA bulk copy of the bootstrapping-key rows
     assert "DFMA" in sass and "USETMAXREG" in sass
+    assert "UTCIMMA" in sass     # tcgen05.mma kind::i8: the key switch
+    assert "LDTM" in sass and "STTM" in sass   # tcgen05.ld / .st: transform exchanges + constants in tensor memory
 
 
 def test_no_gpu_fails_loudly():

@@ -81,3 +81,82 @@ def test_ripple_carry_adder_batch_matches_oracle():
         assert np.array_equal(out[:, :nb], ref)
     finally:
         e.close()
+
+
+def test_schedule_fused_mux_and_comparator():
+    c = Circuit()
+    a = [c.input() for _ in range(4)]
+    b = [c.input() for _ in range(4)]
+    gt = c.greater_than(a, b)
+    eq = c.equals(a, b)
+    c.output(gt); c.output(eq)
+    levels, _ = c.schedule()
+    # xor (1 level) then a chain of 4 fused muxes; the AND tree of equals sits beside it
+    assert len(levels) == 1 + 4
+    assert c.bootstrapped_gate_count() == 2 * 4 + 2 * 4 + 3     # 2 x 4 xors, 4 fused muxes (2 rotations each), 3 ands
+
+
+@pytest.mark.gpu
+def test_fused_mux_is_sound_and_matches_oracle_composition():
+    """Truth table of the fused MUX, and word-for-word equality with the oracle evaluating the same data
+    flow: AND / ANDNY blind rotations, sample_extract_index(., 0) at N = 1024, add + 1/8, one key switch."""
+    from common import keys
+    from rs_tfhe_b200.circuit import evaluate
+    K, ck = keys("128")
+    e = T.CudaBootstrap(T.SECURITY_128_BIT, 0)
+    try:
+        e.load_cloud_key(ck)
+        c = Circuit()
+        s, a, b = c.input(), c.input(), c.input()
+        c.output(c.mux(s, a, b))
+        c.output(c.mux(c.not_(s), a, c.constant(True)))      # free NOT / constant operands
+        combos = np.array([[(v >> i) & 1 for v in range(8)] for i in range(3)], dtype=bool)   # s, a, b
+        reps = 4
+        bits = np.repeat(combos, reps, axis=1)
+        inputs = np.stack([K.encrypt_bool_batch(row, 700 + i) for i, row in enumerate(bits)])
+        out = evaluate(c, e, inputs)
+        assert c.last_stats == {"levels": 1, "bootstraps": 4, "key_switches": 2}
+        sv, av, bv = bits
+        assert np.array_equal(K.decrypt_bool_batch(out[0]), np.where(sv, av, bv))
+        assert np.array_equal(K.decrypt_bool_batch(out[1]), np.where(~sv, av, True))
+        # oracle composition for the first output, every batch element
+        AND, ANDNY = O.GATE_CODE["AND"], O.GATE_CODE["ANDNY"]
+        for j in range(bits.shape[1]):
+            u = []
+            for op, x in ((AND, inputs[1, j]), (ANDNY, inputs[2, j])):
+                ra, rb, _ = K.blind_rotate(K.gate_prep(op, inputs[0, j], x))
+                u.append(O.sample_extract_index(ra, rb, 0))
+            t = (u[0] + u[1]).astype(np.uint32)
+            t[-1] = np.uint32((int(t[-1]) + 0x20000000) & 0xFFFFFFFF)
+            assert np.array_equal(out[0, j], K.identity_key_switching(t)), j
+    finally:
+        e.close()
+
+
+@pytest.mark.gpu
+def test_comparator_batch():
+    from common import keys
+    from rs_tfhe_b200.circuit import evaluate
+    K, ck = keys("128")
+    e = T.CudaBootstrap(T.SECURITY_128_BIT, 0)
+    try:
+        e.load_cloud_key(ck)
+        bits, batch = 8, 40
+        c = Circuit()
+        a = [c.input() for _ in range(bits)]
+        b = [c.input() for _ in range(bits)]
+        c.output(c.greater_than(a, b))
+        c.output(c.equals(a, b))
+        r = np.random.default_rng(8)
+        xa = r.integers(0, 256, batch)
+        xb = r.integers(0, 256, batch)
+        xb[:8] = xa[:8]                                   # some equal pairs
+        xb[8:12] = xa[8:12] ^ 1                           # differ in the lowest bit only
+        in_bits = np.array([[(v >> i) & 1 for v in xa] for i in range(bits)] +
+                           [[(v >> i) & 1 for v in xb] for i in range(bits)], dtype=bool)
+        inputs = np.stack([K.encrypt_bool_batch(row, 800 + i) for i, row in enumerate(in_bits)])
+        out = evaluate(c, e, inputs)
+        assert np.array_equal(K.decrypt_bool_batch(out[0]), xa > xb)
+        assert np.array_equal(K.decrypt_bool_batch(out[1]), xa == xb)
+    finally:
+        e.close()

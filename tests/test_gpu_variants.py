@@ -1,9 +1,9 @@
-"""Every selectable kernel variant stays bit-exact: the experimental blind-rotation variants
-(TFHE_BR_VARIANT=1..8 with the small-batch latency kernel disabled; 8 -- the FFT exchange through
-tensor memory -- is the default throughput variant, 3 the previous one, and TFHE_BR_LATENCY_MAX selects up to which batch size the latency kernel runs) and the key-switch kernels (TFHE_KS_VARIANT=umma -- tcgen05, the default --, mma, rows,
-TFHE_KS_GENERIC=1) run tools/sanitize.py -- mixed gates, LUT bootstrap, blind rotate +
-extract/key switch, each compared word for word with the oracle -- in their own process
-(the selectors are read once per process)."""
+"""Every selectable kernel stays bit-exact: the two throughput blind-rotation shapes (TFHE_BR_VARIANT=8:
+64 threads per ciphertext with a 128-thread partial last round -- the default; 9: 128 threads per ciphertext
+on every round), the latency kernel forced on (TFHE_BR_LATENCY_MAX) and off, and the key-switch kernels
+(TFHE_KS_VARIANT=umma -- tcgen05, the default --, rows, TFHE_KS_GENERIC=1) run tools/sanitize.py -- mixed
+gates, LUT bootstrap, blind rotate + extract/key switch, each compared word for word with the oracle -- in
+their own process (the selectors are read once per process)."""
 import os
 import subprocess
 import sys
@@ -15,13 +15,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize("env", [
-    {"TFHE_BR_VARIANT": "1", "TFHE_BR_LATENCY_MAX": "0"}, {"TFHE_BR_VARIANT": "2", "TFHE_BR_LATENCY_MAX": "0"},
-    {"TFHE_BR_VARIANT": "3", "TFHE_BR_LATENCY_MAX": "0"}, {"TFHE_BR_VARIANT": "4", "TFHE_BR_LATENCY_MAX": "0"},
-    {"TFHE_BR_VARIANT": "5", "TFHE_BR_LATENCY_MAX": "0"}, {"TFHE_BR_VARIANT": "6", "TFHE_BR_LATENCY_MAX": "0"},
-    {"TFHE_BR_VARIANT": "7", "TFHE_BR_LATENCY_MAX": "0"}, {"TFHE_BR_VARIANT": "8", "TFHE_BR_LATENCY_MAX": "0"},
-    {"TFHE_BR_LATENCY_MAX": "1000"},
-    {"TFHE_KS_VARIANT": "umma"}, {"TFHE_KS_VARIANT": "mma"},
-    {"TFHE_KS_VARIANT": "rows"}, {"TFHE_KS_VARIANT": "rows", "TFHE_KS_GENERIC": "1"},
+    {"TFHE_BR_VARIANT": "8", "TFHE_BR_LATENCY_MAX": "0", "SANITIZE_COUNT": "601"},
+    {"TFHE_BR_VARIANT": "9", "TFHE_BR_LATENCY_MAX": "0", "SANITIZE_COUNT": "601"},
+    {"TFHE_BR_VARIANT": "9"}, {"TFHE_BR_LATENCY_MAX": "1000"},
+    {"TFHE_KS_VARIANT": "umma"}, {"TFHE_KS_VARIANT": "rows"}, {"TFHE_KS_VARIANT": "rows", "TFHE_KS_GENERIC": "1"},
 ], ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
 def test_variant_bit_exact(env):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sanitize.py")],

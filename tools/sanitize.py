@@ -8,10 +8,12 @@ K = O.Keys("128", seed=1)
 e = T.CudaBootstrap(T.SECURITY_128_BIT, 0)
 e.load_cloud_key(T.CloudKey(T.SECURITY_128_BIT, K.offset, K.tv_a, K.tv_b, K.ksk, K.bsk))
 rng = O.Rng(2)
-a = np.array([0, 1, 1, 0, 1], dtype=bool); b = np.array([1, 1, 0, 0, 1], dtype=bool)
+count = int(os.environ.get("SANITIZE_COUNT", "5"))   # > 592 reaches the full-round kernel as well
+a = np.resize(np.array([0, 1, 1, 0, 1], dtype=bool), count); b = np.resize(np.array([1, 1, 0, 0, 1], dtype=bool), count)
 pairs = np.stack([K.encrypt_bool(a, rng), K.encrypt_bool(b, rng)], axis=1)
-out = e.batch_gate_mixed(np.array([0, 1, 2, 3, 5], dtype=np.uint8), pairs)
-ref = K.batch_gate(np.array([0, 1, 2, 3, 5], dtype=np.uint8), pairs)
+ops = np.resize(np.array([0, 1, 2, 3, 5], dtype=np.uint8), count)
+out = e.batch_gate_mixed(ops, pairs)
+ref = K.batch_gate(ops, pairs)
 print("gates equal:", np.array_equal(out, ref))
 lut_id, lut_b = e.lut_generate([1, 0], 2)
 ct = K.encrypt_message([1, 0], 2, rng)
