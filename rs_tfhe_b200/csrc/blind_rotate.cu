@@ -651,8 +651,12 @@ BrArgs br_slice(const BrArgs &a, size_t base, size_t n) {
 
 template <int L, int BGBIT>
 cudaError_t launch_t(const BrArgs &args, int num_sms, cudaStream_t stream) {
-  if (L > 1 && args.count <= (size_t)br_latency_threshold(num_sms))
-    return launch_latency<L, BGBIT>(args, num_sms, stream);
+  if (args.count <= (size_t)br_latency_threshold(num_sms)) {
+    // TFHE_BR_LATENCY_KERNEL=x selects the round-1 shape (l groups of 64 threads, gadgets with l > 1)
+    static const bool old_shape = [] { const char *e = getenv("TFHE_BR_LATENCY_KERNEL"); return e && e[0] == 'x'; }();
+    if (args.bsk3 && !old_shape) return br_launch_latency_s(L, BGBIT, args, num_sms, stream);
+    if (L > 1) return launch_latency<L, BGBIT>(args, num_sms, stream);
+  }
   // 9: 128 threads per ciphertext, all-FMA radix 4/8/4/4 passes (blind_rotate_s.cu), every round
   if (br_variant() == 9) return br_launch_s(L, BGBIT, args, num_sms, stream);
   // 8 (default): full persistent rounds (4 ciphertexts per SM) on the 64-thread kernel -- pass B<->C
@@ -688,7 +692,7 @@ cudaError_t br_launch(uint32_t l, uint32_t bgbit, const BrArgs &args, int num_sm
   if (launched) {   // kernels this call puts on the stream (the default shape may split off a tail launch)
     const size_t round = (size_t)num_sms * 4, tail = args.count % round;
     const bool split = br_variant() == 8 && args.count > round && tail != 0 && tail <= (size_t)num_sms * 3 &&
-                       args.bsk3 && !(l > 1 && args.count <= (size_t)br_latency_threshold(num_sms));
+                       args.bsk3 && !(args.count <= (size_t)br_latency_threshold(num_sms));
     *launched = args.count == 0 ? 0 : split ? 2 : 1;
   }
   if (args.count == 0) return cudaSuccess;

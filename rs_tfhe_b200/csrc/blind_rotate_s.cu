@@ -230,7 +230,232 @@ cudaError_t launch_s(const BrArgs &args_in, int num_sms, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+// ---- latency shape: ONE ciphertext per CTA, spread over l groups of 128 threads ---------------------
+// Dependent PBS chains (BASELINE config 4: examples/lut_add_two_numbers.rs:80-157) and batches of at
+// most one ciphertext per SM are bound by the latency of a single blind rotation.  Group g of l takes
+// digit g of BOTH accumulator polynomials (key rows g and l + g of BSK[i]): two forward transforms and
+// two MACs instead of 2l, the groups' partial spectra meet in shared memory, and groups 0 and 1 run the
+// two inverse transforms in parallel.  The ring has one stage per key row, each consumed by exactly
+// one group, so the next step's rows stream in during the inverse (and the producer prefetches the
+// step after into L2: a lone ciphertext streams the key cold from HBM).  l * 128 + 32 threads,
+// 128 registers each without rebalancing (4 warps per sub-partition).
+template <int L, int BGBIT, bool MAGIC>
+__global__ void __launch_bounds__(L * brs::kT + 32, 1) blind_rotate_latency_s_kernel(const BrArgs args) {
+  constexpr int NG = L, L2 = 2 * L, STAGES = L2;
+  constexpr int kCons = NG * brs::kT;
+  constexpr bool EXACT = (L == 3 && BGBIT == 6);
+  constexpr int kAccBytes = 2 * kN * 4;
+  constexpr int kInvBytes = 8 * brs::kInvPitch * 16;
+  constexpr int kExchBytes = 2 * kHalf * 16;                      // two forward buffers (>= one inverse buffer)
+  constexpr int kPartBytes = 2 * 4 * brs::kT * 16;                // one group's partial spectra [o][kd][T]
+  static_assert(kInvBytes <= kExchBytes, "inverse buffer aliases the forward buffers");
+  extern __shared__ __align__(128) uint8_t smem[];
+  cplx *ring = reinterpret_cast<cplx *>(smem);
+  uint32_t *acc = reinterpret_cast<uint32_t *>(smem + STAGES * kStageBytes);
+  uint8_t *exch_base = smem + STAGES * kStageBytes + kAccBytes;
+  cplx *part = reinterpret_cast<cplx *>(exch_base + NG * kExchBytes);
+  uint16_t *abar_s = reinterpret_cast<uint16_t *>(exch_base + NG * (kExchBytes + kPartBytes));
+  uint64_t *full = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(abar_s) + 2432);
+  uint64_t *empty = full + STAGES;
+  uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(empty + STAGES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t n = args.n, grid = gridDim.x;
+  const uint32_t rounds = (uint32_t)((args.count + grid - 1) / grid);
+  if (threadIdx.x == 0) {
+    for (int r = 0; r < STAGES; r++) { mbar_init(&full[r], 1); mbar_init(&empty[r], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc_512(tmem_base_s);
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tbase = *tmem_base_s;
+  if (warp >= 4 * NG) {
+    if (lane == 0) {
+      const uint8_t *src0 = reinterpret_cast<const uint8_t *>(args.bsk3);
+      uint32_t parity = 0;
+      for (uint32_t rd = 0; rd < rounds; rd++)
+        for (uint32_t i = 0; i < n; i++) {
+          for (uint32_t r = 0; r < (uint32_t)L2; r++) {
+            mbar_wait_backoff(&empty[r], parity ^ 1, 64);
+            mbar_arrive_expect_tx(&full[r], kStageBytes);
+            tma_load_1d(reinterpret_cast<uint8_t *>(ring) + r * kStageBytes,
+                        src0 + ((size_t)i * L2 + r) * kStageBytes, kStageBytes, &full[r]);
+            if (i + 1 < n)
+              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(
+                               src0 + ((size_t)(i + 1) * L2 + r) * kStageBytes),
+                           "n"(kStageBytes)
+                           : "memory");
+          }
+          parity ^= 1;
+        }
+    }
+    return;
+  }
+  const int g = warp >> 2;
+  const int T = threadIdx.x & (brs::kT - 1);
+  const int ctid = threadIdx.x;                      // 0 .. kCons-1 among the consumers
+  cplx *exch = reinterpret_cast<cplx *>(exch_base + g * kExchBytes);
+  auto cta_sync = [&]() { asm volatile("bar.sync 8, %0;" ::"n"(kCons) : "memory"); };
+  const uint32_t taddr = tbase + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)g * 128u;
+  const uint32_t t_b = taddr, t_cd = taddr + 16, t_cbi = taddr + 32, t_ai = taddr + 48, t_ut = taddr + 64;
+  const uint32_t tq0 = taddr + 80, tq1 = taddr + 96;
+  {
+    const cplx *tw = args.tw_s + (size_t)T * brs::kTwPerThread;
+#pragma unroll
+    for (int blk = 0; blk < 5; blk++) {
+      cplx t[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) t[k] = tw[4 * blk + k];
+      tm_store4(taddr + 16 * blk, t);
+    }
+    tm_wait_st();
+  }
+  uint32_t parity = 0;
+  for (uint32_t rd = 0; rd < rounds; rd++) {
+    const size_t ct = (size_t)rd * grid + blockIdx.x;
+    const bool active = ct < args.count;
+    if (active) prologue<kCons>(args, ct, ctid, abar_s, acc);
+    cta_sync();
+    for (uint32_t i = 0; i < n; i++) {
+      if (active) {
+        const uint32_t abar = abar_s[i];
+        cplx racc[2][4];
+#pragma unroll
+        for (int o = 0; o < 2; o++)
+#pragma unroll
+          for (int k = 0; k < 4; k++) racc[o][k] = mk(0.0, 0.0);
+#pragma unroll
+        for (int p = 0; p < 2; p++) {   // digit g of both accumulator polynomials
+          uint32_t t_re[4], t_im[4];
+          brs::load_t(T, acc + p * kN, abar, args.offset, t_re, t_im);
+          brs::fwd_pass_a<BGBIT, MAGIC>(T, g, t_re, t_im, exch + p * kHalf);
+        }
+        named_sync<brs::kT>(g + 1);
+        {
+          cplx tb[4], tcd[4];
+          tm_load4(t_b, tb);
+          tm_load4(t_cd, tcd);
+#pragma unroll
+          for (int p = 0; p < 2; p++) {
+            const int row = p * L + g;
+            cplx y[4];
+            brs::fwd_pass_b(T, exch + p * kHalf, tb[0], tb[1], tb[2], y);
+            xchg_fwd(tq0, y);
+            brs::r4<false>(y, tcd[0], tcd[1]);
+            xchg_fwd(tq1, y);
+            brs::r4<false>(y, tcd[2], tcd[3]);
+            mbar_wait(&full[row], parity);
+            const cplx *rw = ring + row * brs::kRowCplx + T;
+#pragma unroll
+            for (int kd = 0; kd < 4; kd++) {
+              cfma(racc[0][kd], y[kd], rw[(kd * 2 + 0) * brs::kT]);
+              cfma(racc[1][kd], y[kd], rw[(kd * 2 + 1) * brs::kT]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[row]);
+          }
+        }
+        if (NG > 1) {
+          // publish this group's partial spectra; group o sums output o and runs its inverse
+          cplx *mine = part + (size_t)g * (2 * 4 * brs::kT);
+#pragma unroll
+          for (int o = 0; o < 2; o++)
+#pragma unroll
+            for (int kd = 0; kd < 4; kd++) mine[(o * 4 + kd) * brs::kT + T] = racc[o][kd];
+          cta_sync();   // partials visible; every group is past its pass-B reads of the exchange buffers
+          if (g < 2) {
+            cplx s[4];
+#pragma unroll
+            for (int kd = 0; kd < 4; kd++) s[kd] = g ? racc[1][kd] : racc[0][kd];   // no dynamic register indexing
+#pragma unroll
+            for (int gg = 0; gg < NG; gg++) {
+              if (gg == g) continue;
+              const cplx *src = part + (size_t)gg * (2 * 4 * brs::kT) + (size_t)g * 4 * brs::kT + T;
+#pragma unroll
+              for (int kd = 0; kd < 4; kd++) s[kd] = cadd(s[kd], src[kd * brs::kT]);
+            }
+            cplx ti[4];
+            tm_load4(t_cbi, ti);
+            brs::r4_plain<true>(s);
+            xchg_inv(tq0, s);
+            brs::r4<true>(s, ti[0], ti[1]);
+            xchg_inv(tq1, s);
+            brs::r4<true>(s, ti[2], ti[3]);
+            brs::inv_store_b(T, s, exch);
+            named_sync<brs::kT>(g + 1);
+            cplx ta[4], ut[4];
+            tm_load4(t_ai, ta);
+            tm_load4(t_ut, ut);
+            brs::inv_pass_a<EXACT, MAGIC>(T, exch, ta[0], ta[1], ta[2], ut, acc + g * kN);
+          }
+          cta_sync();
+        } else {
+          named_sync<brs::kT>(g + 1);   // pass-B reads done: the exchange buffers may be rewritten
+          cplx ti[4];
+          tm_load4(t_cbi, ti);
+#pragma unroll
+          for (int o = 0; o < 2; o++) {
+            brs::r4_plain<true>(racc[o]);
+            xchg_inv(tq0, racc[o]);
+            brs::r4<true>(racc[o], ti[0], ti[1]);
+            xchg_inv(tq1, racc[o]);
+            brs::r4<true>(racc[o], ti[2], ti[3]);
+            brs::inv_store_b(T, racc[o], exch);
+            named_sync<brs::kT>(g + 1);
+            cplx ta[4], ut[4];
+            tm_load4(t_ai, ta);
+            tm_load4(t_ut, ut);
+            brs::inv_pass_a<EXACT, MAGIC>(T, exch, ta[0], ta[1], ta[2], ut, acc + o * kN);
+            named_sync<brs::kT>(g + 1);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+          const int row = p * L + g;
+          mbar_wait(&full[row], parity);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[row]);
+        }
+      }
+      parity ^= 1;
+    }
+    if (active) epilogue<kCons>(args, ct, ctid, acc);
+    cta_sync();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cta_sync();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (warp == 0) tmem_dealloc_512(tbase);
+}
+
+template <int L, int BGBIT>
+cudaError_t launch_latency_s(const BrArgs &args, int num_sms, cudaStream_t stream) {
+  constexpr bool MAGIC = (L == 3 && BGBIT == 6);
+  if (!args.bsk3 || !args.tw_s) return cudaErrorInvalidValue;
+  auto kern = blind_rotate_latency_s_kernel<L, BGBIT, MAGIC>;
+  const int smem = 2 * L * kStageBytes + 2 * kN * 4 + L * (2 * kHalf * 16 + 2 * 4 * brs::kT * 16) + 2432 +
+                   2 * 2 * L * 8 + 16;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  int grid = (int)(args.count < (size_t)num_sms ? args.count : (size_t)num_sms);
+  if (grid < 1) grid = 1;
+  kern<<<grid, L * brs::kT + 32, smem, stream>>>(args);
+  return cudaGetLastError();
+}
+
 }  // namespace
+
+cudaError_t br_launch_latency_s(uint32_t l, uint32_t bgbit, const BrArgs &args, int num_sms, cudaStream_t stream) {
+  if (args.count == 0) return cudaSuccess;
+  if (l == 3 && bgbit == 6) return launch_latency_s<3, 6>(args, num_sms, stream);
+  if (l == 2 && bgbit == 10) return launch_latency_s<2, 10>(args, num_sms, stream);
+  if (l == 1 && bgbit == 18) return launch_latency_s<1, 18>(args, num_sms, stream);
+  if (l == 1 && bgbit == 22) return launch_latency_s<1, 22>(args, num_sms, stream);
+  if (l == 1 && bgbit == 23) return launch_latency_s<1, 23>(args, num_sms, stream);
+  return cudaErrorInvalidValue;
+}
 
 cudaError_t br_launch_s(uint32_t l, uint32_t bgbit, const BrArgs &args, int num_sms, cudaStream_t stream) {
   if (args.count == 0) return cudaSuccess;

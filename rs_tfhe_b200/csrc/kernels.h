@@ -34,6 +34,9 @@ bool br_uses_permuted_key();  // the selected throughput kernel reads BrArgs::bs
 bool br_uses_s_key();         // the selected throughput kernel reads BrArgs::bsk3 / tw_s
 cudaError_t br_launch(uint32_t l, uint32_t bgbit, const BrArgs &args, int num_sms,
                       cudaStream_t stream, int *launched = nullptr);
+// one ciphertext per CTA over l groups of 128 threads (blind_rotate_s.cu): small batches, dependent chains
+cudaError_t br_launch_latency_s(uint32_t l, uint32_t bgbit, const BrArgs &args, int num_sms,
+                                cudaStream_t stream);
 // 128-thread-per-ciphertext throughput kernel (blind_rotate_s.cu)
 cudaError_t br_launch_s(uint32_t l, uint32_t bgbit, const BrArgs &args, int num_sms,
                         cudaStream_t stream);
