@@ -430,6 +430,287 @@ __global__ void __launch_bounds__(L * brs::kT + 32, 1) blind_rotate_latency_s_ke
   if (warp == 0) tmem_dealloc_512(tbase);
 }
 
+// ---- cluster latency shape: ONE ciphertext per thread-block CLUSTER of two CTAs -----------------------
+// For chains of dependent bootstraps a lone blind rotation is bound by what one SM can issue per step
+// (measured: every phase of the one-CTA latency shape is issue / FP64-pipe bound).  Two CTAs on two SMs
+// split the step: CTA c owns accumulator polynomial c -- it rotates / decomposes / transforms only that
+// polynomial (digit g in group g: key row c*l + g), so the forward work per SM halves -- and output c:
+// the partial spectra for the OTHER output go straight into the peer's shared memory
+// (st.shared::cluster, distributed shared memory) and a remote mbarrier arrive tells the peer they
+// landed; each CTA then sums 2l partials for its own output, runs ONE inverse transform and updates its
+// own polynomial, which is all it needs for the next step: no accumulator data ever crosses.
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_remote(uint32_t addr, cplx v) {
+  asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int L, int BGBIT, bool MAGIC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L * brs::kT + 32, 1)
+blind_rotate_cluster_kernel(const BrArgs args) {
+  constexpr int NG = L, STAGES = L;
+  constexpr int kCons = NG * brs::kT;
+  constexpr bool EXACT = (L == 3 && BGBIT == 6);
+  constexpr int kInvBytes = 8 * brs::kInvPitch * 16;              // >= one forward buffer (8 KB)
+  constexpr int kSlotCplx = 4 * brs::kT;                           // one group's partial spectrum of one output
+  constexpr int kPartBytes = 2 * L * kSlotCplx * 16;               // 2l slots: l local + l from the peer
+  extern __shared__ __align__(128) uint8_t smem[];
+  cplx *ring = reinterpret_cast<cplx *>(smem);
+  uint32_t *acc = reinterpret_cast<uint32_t *>(smem + STAGES * kStageBytes);        // OUR polynomial only
+  uint8_t *exch_base = smem + STAGES * kStageBytes + kN * 4;
+  cplx *part = reinterpret_cast<cplx *>(exch_base + NG * kInvBytes);               // [parity 2][2l][4][128]
+  // part: [parity 2][2l local slots][4][128], then [parity 2] reduced spectra received from the peer
+  uint16_t *abar_s = reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(part) + 2 * kPartBytes + 2 * kSlotCplx * 16);
+  uint64_t *full = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(abar_s) + 2432);
+  uint64_t *empty = full + STAGES;
+  uint64_t *xbar = empty + STAGES;                                 // [2]: the peer's reduced spectrum of this parity landed
+  uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(xbar + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t n = args.n;
+  const uint32_t rank = cluster_rank(), peer = rank ^ 1u;
+  const uint32_t n_clusters = gridDim.x >> 1, cluster = blockIdx.x >> 1;
+  const uint32_t rounds = (uint32_t)((args.count + n_clusters - 1) / n_clusters);
+  if (threadIdx.x == 0) {
+    for (int r = 0; r < STAGES; r++) { mbar_init(&full[r], 1); mbar_init(&empty[r], 4); }
+    mbar_init(&xbar[0], 4); mbar_init(&xbar[1], 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc_512(tmem_base_s);
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  cluster_sync_all();            // the peer's mbarriers exist before anyone arrives on them remotely
+  const uint32_t tbase = *tmem_base_s;
+  if (warp >= 4 * NG) {
+    if (lane == 0) {
+      const uint8_t *src0 = reinterpret_cast<const uint8_t *>(args.bsk3);
+      uint32_t parity = 0;
+      for (uint32_t rd = 0; rd < rounds; rd++)
+        for (uint32_t i = 0; i < n; i++) {
+          for (uint32_t r = 0; r < (uint32_t)L; r++) {
+            const size_t row = (size_t)i * 2 * L + rank * L + r;
+            mbar_wait_backoff(&empty[r], parity ^ 1, 64);
+            mbar_arrive_expect_tx(&full[r], kStageBytes);
+            tma_load_1d(reinterpret_cast<uint8_t *>(ring) + r * kStageBytes, src0 + row * kStageBytes, kStageBytes,
+                        &full[r]);
+            if (i + 1 < n)
+              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src0 + (row + 2 * L) * kStageBytes),
+                           "n"(kStageBytes)
+                           : "memory");
+          }
+          parity ^= 1;
+        }
+    }
+    return;
+  }
+  const int g = warp >> 2;
+  const int T = threadIdx.x & (brs::kT - 1);
+  const int ctid = threadIdx.x;
+  cplx *exch = reinterpret_cast<cplx *>(exch_base + g * kInvBytes);
+  auto cta_sync = [&]() { asm volatile("bar.sync 8, %0;" ::"n"(kCons) : "memory"); };
+  const uint32_t taddr = tbase + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)g * 128u;
+  const uint32_t t_b = taddr, t_cd = taddr + 16, t_cbi = taddr + 32, t_ai = taddr + 48, t_ut = taddr + 64;
+  const uint32_t tq0 = taddr + 80, tq1 = taddr + 96;
+  {
+    const cplx *tw = args.tw_s + (size_t)T * brs::kTwPerThread;
+#pragma unroll
+    for (int blk = 0; blk < 5; blk++) {
+      cplx t[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) t[k] = tw[4 * blk + k];
+      tm_store4(taddr + 16 * blk, t);
+    }
+    tm_wait_st();
+  }
+  const uint32_t part_remote = map_to_cta(smem_u32(part), peer);
+  const uint32_t xbar_remote = map_to_cta(smem_u32(xbar), peer);
+  uint32_t parity = 0, step = 0;     // step counts CMUX steps over all rounds: partial buffers alternate by step
+  for (uint32_t rd = 0; rd < rounds; rd++) {
+    const size_t ct = (size_t)rd * n_clusters + cluster;
+    const bool active = ct < args.count;      // both CTAs of a cluster agree
+    if (active) {
+      // K0 for our polynomial: abar for every step, acc = (X^b~ * testvec)[rank]
+      const uint32_t w = n + 1;
+      uint32_t ca = 1, cb = 0, off = 0;
+      const uint32_t *A, *B;
+      if (args.op >= 0 || args.ops) {
+        int op = args.ops ? (int)args.ops[ct] : args.op;
+        if ((unsigned)op >= (unsigned)TFHE_GATE_COUNT) op = 0;
+        ca = (uint32_t)c_gate_ca[op]; cb = (uint32_t)c_gate_cb[op]; off = c_gate_off[op];
+        A = args.in + ct * 2 * w; B = A + w;
+      } else {
+        A = args.in + ct * w; B = A;
+      }
+      for (uint32_t x = ctid; x < n; x += kCons) {
+        const uint32_t v = ca * A[x] + cb * B[x];
+        abar_s[x] = (uint16_t)((uint32_t)(v + (1u << 20)) >> 21);
+      }
+      const uint32_t bw = ca * A[n] + cb * B[n] + off;
+      const uint32_t b_tilda = (uint32_t)(2 * kN - (((uint64_t)bw + (1u << 20)) >> 21));
+      const int tvi = args.tv_index ? args.tv_index[ct] : args.tv_default;
+      const uint32_t *tv = args.tv + ((size_t)tvi * 2 + rank) * kN;
+      for (int x = ctid; x < kN; x += kCons) acc[x] = rot_coeff(tv, x, b_tilda);
+    }
+    cta_sync();
+    for (uint32_t i = 0; i < n; i++, step++) {
+      const uint32_t par = step & 1u, xphase = (step >> 1) & 1u;
+      if (active) {
+        const uint32_t abar = abar_s[i];
+        cplx racc[2][4];
+#pragma unroll
+        for (int o = 0; o < 2; o++)
+#pragma unroll
+          for (int k = 0; k < 4; k++) racc[o][k] = mk(0.0, 0.0);
+        {
+          uint32_t t_re[4], t_im[4];
+          brs::load_t(T, acc, abar, args.offset, t_re, t_im);
+          brs::fwd_pass_a<BGBIT, MAGIC>(T, g, t_re, t_im, exch);
+        }
+        named_sync<brs::kT>(g + 1);
+        {
+          cplx tb[4], tcd[4], y[4];
+          tm_load4(t_b, tb);
+          tm_load4(t_cd, tcd);
+          brs::fwd_pass_b(T, exch, tb[0], tb[1], tb[2], y);
+          xchg_fwd(tq0, y);
+          brs::r4<false>(y, tcd[0], tcd[1]);
+          xchg_fwd(tq1, y);
+          brs::r4<false>(y, tcd[2], tcd[3]);
+          mbar_wait(&full[g], parity);
+          const cplx *rw = ring + g * brs::kRowCplx + T;
+#pragma unroll
+          for (int kd = 0; kd < 4; kd++) {
+            cfma(racc[0][kd], y[kd], rw[(kd * 2 + 0) * brs::kT]);
+            cfma(racc[1][kd], y[kd], rw[(kd * 2 + 1) * brs::kT]);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[g]);
+        }
+        // Both outputs' partials go to local slots [o][g]; then the LAST group sums the peer's output over
+        // the l groups and ships ONE 8 KB spectrum through distributed shared memory (DSMEM moves only
+        // ~20 B/clk, so the l partials are reduced before they cross), while group 0 sums our own output.
+        {
+          cplx *mine = part + (size_t)par * (2 * L * kSlotCplx) + (size_t)g * kSlotCplx + T;
+#pragma unroll
+          for (int kd = 0; kd < 4; kd++) {
+            mine[kd * brs::kT] = rank ? racc[1][kd] : racc[0][kd];                                  // ours: slots 0..l-1
+            mine[(size_t)L * kSlotCplx + kd * brs::kT] = rank ? racc[0][kd] : racc[1][kd];        // peer's: slots l..2l-1
+          }
+        }
+        cta_sync();   // local partials visible; forward exchange buffers free
+        if (g == NG - 1) {
+          const cplx *src = part + (size_t)par * (2 * L * kSlotCplx) + (size_t)L * kSlotCplx + T;
+          const uint32_t dst = part_remote + (uint32_t)((2 * (size_t)2 * L * kSlotCplx + (size_t)par * kSlotCplx + T) * 16);
+#pragma unroll
+          for (int kd = 0; kd < 4; kd++) {
+            cplx v = src[kd * brs::kT];
+#pragma unroll
+            for (int sl = 1; sl < L; sl++) v = cadd(v, src[(size_t)sl * kSlotCplx + kd * brs::kT]);
+            st_remote(dst + (uint32_t)(kd * brs::kT * 16), v);
+          }
+          asm volatile("fence.acq_rel.cluster;" ::: "memory");   // every lane's remote stores before the warp's arrive
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(xbar_remote + 8u * par);
+        }
+        if (g == 0) {
+          cplx s[4];
+          const cplx *src = part + (size_t)par * (2 * L * kSlotCplx) + T;
+#pragma unroll
+          for (int kd = 0; kd < 4; kd++) s[kd] = src[kd * brs::kT];
+#pragma unroll
+          for (int sl = 1; sl < L; sl++)
+#pragma unroll
+            for (int kd = 0; kd < 4; kd++) s[kd] = cadd(s[kd], src[(size_t)sl * kSlotCplx + kd * brs::kT]);
+          mbar_wait_cluster(&xbar[par], xphase);
+          const cplx *rem = part + 2 * (size_t)2 * L * kSlotCplx + (size_t)par * kSlotCplx + T;   // the peer's reduced spectrum
+#pragma unroll
+          for (int kd = 0; kd < 4; kd++) s[kd] = cadd(s[kd], rem[kd * brs::kT]);
+          cplx ti[4];
+          tm_load4(t_cbi, ti);
+          brs::r4_plain<true>(s);
+          xchg_inv(tq0, s);
+          brs::r4<true>(s, ti[0], ti[1]);
+          xchg_inv(tq1, s);
+          brs::r4<true>(s, ti[2], ti[3]);
+          brs::inv_store_b(T, s, exch);
+          named_sync<brs::kT>(1);
+          cplx ta[4], ut[4];
+          tm_load4(t_ai, ta);
+          tm_load4(t_ut, ut);
+          brs::inv_pass_a<EXACT, MAGIC>(T, exch, ta[0], ta[1], ta[2], ut, acc);
+        }
+        cta_sync();
+      } else {
+        mbar_wait(&full[g], parity);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[g]);
+      }
+      parity ^= 1;
+    }
+    if (active) {
+      // epilogue: every mode's output splits cleanly by polynomial (trlwe.rs:106-136)
+      if (args.out_mode == BR_OUT_TRLWE) {
+        uint32_t *o = args.out + ct * 2 * kN + rank * kN;
+        for (int x = ctid; x < kN; x += kCons) o[x] = acc[x];
+      } else {
+        const uint32_t m = args.out_mode == BR_OUT_EXTRACT ? (uint32_t)kN : n;
+        uint32_t *o = args.out + ct * (m + 1);
+        if (rank == 0) {
+          for (uint32_t x = ctid; x < m; x += kCons) o[x] = x == 0 ? acc[0] : ~acc[m - x];
+        } else if (ctid == 0) {
+          o[m] = acc[0];
+        }
+      }
+    }
+    cta_sync();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cta_sync();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (warp == 0) tmem_dealloc_512(tbase);
+}
+
+template <int L, int BGBIT>
+cudaError_t launch_cluster(const BrArgs &args, int num_sms, cudaStream_t stream) {
+  constexpr bool MAGIC = (L == 3 && BGBIT == 6);
+  if (!args.bsk3 || !args.tw_s) return cudaErrorInvalidValue;
+  auto kern = blind_rotate_cluster_kernel<L, BGBIT, MAGIC>;
+  const int smem = L * kStageBytes + kN * 4 + L * (8 * brs::kInvPitch * 16) + 2 * (2 * L * 4 * brs::kT * 16) +
+                   2 * (4 * brs::kT * 16) + 2432 + (2 * L + 2) * 8 + 16;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  int clusters = (int)(args.count < (size_t)(num_sms / 2) ? args.count : (size_t)(num_sms / 2));
+  if (clusters < 1) clusters = 1;
+  kern<<<2 * clusters, L * brs::kT + 32, smem, stream>>>(args);   // __cluster_dims__(2): pairs of CTAs
+  return cudaGetLastError();
+}
+
 template <int L, int BGBIT>
 cudaError_t launch_latency_s(const BrArgs &args, int num_sms, cudaStream_t stream) {
   constexpr bool MAGIC = (L == 3 && BGBIT == 6);
@@ -446,6 +727,16 @@ cudaError_t launch_latency_s(const BrArgs &args, int num_sms, cudaStream_t strea
 }
 
 }  // namespace
+
+cudaError_t br_launch_cluster(uint32_t l, uint32_t bgbit, const BrArgs &args, int num_sms, cudaStream_t stream) {
+  if (args.count == 0) return cudaSuccess;
+  if (l == 3 && bgbit == 6) return launch_cluster<3, 6>(args, num_sms, stream);
+  if (l == 2 && bgbit == 10) return launch_cluster<2, 10>(args, num_sms, stream);
+  if (l == 1 && bgbit == 18) return launch_cluster<1, 18>(args, num_sms, stream);
+  if (l == 1 && bgbit == 22) return launch_cluster<1, 22>(args, num_sms, stream);
+  if (l == 1 && bgbit == 23) return launch_cluster<1, 23>(args, num_sms, stream);
+  return cudaErrorInvalidValue;
+}
 
 cudaError_t br_launch_latency_s(uint32_t l, uint32_t bgbit, const BrArgs &args, int num_sms, cudaStream_t stream) {
   if (args.count == 0) return cudaSuccess;

@@ -37,6 +37,9 @@ cudaError_t br_launch(uint32_t l, uint32_t bgbit, const BrArgs &args, int num_sm
 // one ciphertext per CTA over l groups of 128 threads (blind_rotate_s.cu): small batches, dependent chains
 cudaError_t br_launch_latency_s(uint32_t l, uint32_t bgbit, const BrArgs &args, int num_sms,
                                 cudaStream_t stream);
+// one ciphertext per 2-CTA thread-block cluster, partial spectra exchanged through distributed shared memory
+cudaError_t br_launch_cluster(uint32_t l, uint32_t bgbit, const BrArgs &args, int num_sms,
+                              cudaStream_t stream);
 // 128-thread-per-ciphertext throughput kernel (blind_rotate_s.cu)
 cudaError_t br_launch_s(uint32_t l, uint32_t bgbit, const BrArgs &args, int num_sms,
                         cudaStream_t stream);

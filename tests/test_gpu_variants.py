@@ -17,7 +17,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.mark.parametrize("env", [
     {"TFHE_BR_VARIANT": "8", "TFHE_BR_LATENCY_MAX": "0", "SANITIZE_COUNT": "601"},
     {"TFHE_BR_VARIANT": "9", "TFHE_BR_LATENCY_MAX": "0", "SANITIZE_COUNT": "601"},
-    {"TFHE_BR_VARIANT": "9"}, {"TFHE_BR_LATENCY_MAX": "1000"},
+    {"TFHE_BR_VARIANT": "9"}, {"TFHE_BR_LATENCY_MAX": "1000"}, {"TFHE_BR_CLUSTER": "1"},
+    {"TFHE_BR_LATENCY_KERNEL": "x"},
     {"TFHE_KS_VARIANT": "umma"}, {"TFHE_KS_VARIANT": "rows"}, {"TFHE_KS_VARIANT": "rows", "TFHE_KS_GENERIC": "1"},
 ], ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
 def test_variant_bit_exact(env):
