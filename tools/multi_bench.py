@@ -23,7 +23,7 @@ for nd in sorted({1, n_dev}):
     e = T.CudaBootstrap(P, list(range(nd)))
     e.load_cloud_key(ck)
     e.load_cloud_key(ck)                                   # second load: communicator already warm
-    out = e.batch_gate_mixed(ops[:4096 * nd], pairs[:4096 * nd])   # warm-up (allocations)
+    out = e.batch_gate_mixed(ops[:16384 * nd], pairs[:16384 * nd])   # warm-up (device + pinned staging allocations)
     t = time.perf_counter()
     out = e.batch_gate_mixed(ops, pairs)
     dt = time.perf_counter() - t
