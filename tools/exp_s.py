@@ -29,7 +29,7 @@ for c in configs:
         k, v = kv.split("=")
         env[k] = v
     try:
-        p = subprocess.run([sys.executable, __file__, "--child", count], env=env, capture_output=True, text=True, timeout=120)
+        p = subprocess.run([sys.executable, __file__, "--child", count], env=env, capture_output=True, text=True, timeout=int(os.environ.get("EXP_TIMEOUT", "120")))
         line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
         res[c] = json.loads(line[0][7:]) if line else {"error": (p.stderr or p.stdout)[-400:]}
     except subprocess.TimeoutExpired:
