@@ -110,6 +110,10 @@ int tfhe_engine_last_kernel_ms(tfhe_engine *e, float out_ms[2]);
 /* Diagnostic (roofline denominator): sustained FP64 FMA rate of the engine's GPU,
  * measured now with a register-only DFMA kernel; TFLOP/s (2 flop per FMA). */
 int tfhe_probe_fp64_tflops(tfhe_engine *e, double *tflops_out);
+/* The same with three distinct register operands per FMA (d = a * b + d), which is what the blind
+ * rotation issues (per-lane twiddles and key values).  B200 feeds its FP64 unit one 64-bit operand
+ * per lane per cycle, so this is 2/3 of the figure above (profiles/r2_fp64_operand_probe.json). */
+int tfhe_probe_fp64_3op_tflops(tfhe_engine *e, double *tflops_out);
 
 /* ---- cloud key ----------------------------------------------------------- */
 /* Replaces: the CloudKey a caller passes to every gate (key.rs:51-56).  Takes

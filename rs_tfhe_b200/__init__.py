@@ -178,6 +178,7 @@ def _load():
     L.tfhe_engine_import_cloud_key.argtypes = [vp, vp, C.c_size_t]
     L.tfhe_engine_generate_cloud_key.argtypes = [vp, u32p, u32p, C.c_double, C.c_double, C.c_uint64]
     L.tfhe_probe_fp64_tflops.argtypes = [vp, C.POINTER(C.c_double)]
+    L.tfhe_probe_fp64_3op_tflops.argtypes = [vp, C.POINTER(C.c_double)]
     if L.tfhe_abi_version() != 2:
         raise EngineError("libtfhe_b200.so ABI version mismatch")
     _lib = L
@@ -338,6 +339,12 @@ class CudaBootstrap:
         """Measured DFMA rate of this GPU (roofline denominator for the FP64-bound kernel)."""
         v = C.c_double(0.0)
         _check(_load().tfhe_probe_fp64_tflops(self._h, C.byref(v)))
+        return v.value
+
+    def probe_fp64_3op_tflops(self) -> float:
+        """The same with three distinct register operands per DFMA (the blind rotation's operand pattern)."""
+        v = C.c_double(0.0)
+        _check(_load().tfhe_probe_fp64_3op_tflops(self._h, C.byref(v)))
         return v.value
 
     # ---- Bootstrap trait (batched: accepts [n+1] or [count][n+1])

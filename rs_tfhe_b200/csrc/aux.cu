@@ -118,10 +118,36 @@ __global__ void fp64_probe_kernel(double *sink, int iters) {
   if (r == 123.456) sink[0] = r;  // never true; keeps the chains alive
 }
 
+// The same stream with three DISTINCT register operands per DFMA (d_i = a_i * b_i + d_i): what the
+// blind rotation's butterflies and MACs look like to the register file -- every lane holds its own
+// twiddle and key value.  On B200 this runs at 2/3 of the rate above: the FP64 unit receives one
+// 64-bit operand per lane per cycle (tools/probe/dfma_operand_probe.cu, profiles/r2_fp64_operand_probe.json).
+__global__ void fp64_probe3_kernel(double *sink, int iters) {
+  double a[8], b[8], d[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    a[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+    b[i] = 1.0 - 1e-9 * (threadIdx.x + 2 * i);
+    d[i] = 1e-9 * (i + 3);
+  }
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+      for (int i = 0; i < 8; i++) asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(d[i]) : "d"(a[i]), "d"(b[i]));
+  }
+  double r = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r += d[i] + a[i] + b[i];
+  if (r == 123.456) sink[0] = r;
+}
+
 }  // namespace
 
-cudaError_t fp64_probe_launch(double *d_sink, int blocks, int iters, cudaStream_t stream) {
-  fp64_probe_kernel<<<blocks, 256, 0, stream>>>(d_sink, iters);
+cudaError_t fp64_probe_launch(double *d_sink, int blocks, int iters, bool three_operands, cudaStream_t stream) {
+  if (three_operands) fp64_probe3_kernel<<<blocks, 256, 0, stream>>>(d_sink, iters);
+  else fp64_probe_kernel<<<blocks, 256, 0, stream>>>(d_sink, iters);
   return cudaGetLastError();
 }
 

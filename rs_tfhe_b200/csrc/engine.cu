@@ -721,7 +721,7 @@ int tfhe_engine_last_kernel_ms(tfhe_engine *e, float out_ms[2]) {
   return TFHE_OK;
 }
 
-int tfhe_probe_fp64_tflops(tfhe_engine *e, double *tflops_out) {
+static int probe_fp64(tfhe_engine *e, bool three_operands, double *tflops_out) {
   if (!e || !tflops_out) return fail(TFHE_ERR_INVALID, "null argument");
   std::lock_guard<std::mutex> lock(e->mu);
   CU(cudaSetDevice(e->dev));
@@ -730,7 +730,7 @@ int tfhe_probe_fp64_tflops(tfhe_engine *e, double *tflops_out) {
   double best = 0.0;
   for (int rep = 0; rep < 4; rep++) {
     CU(cudaEventRecord(e->ev[3], e->stream));
-    CU(fp64_probe_launch(static_cast<double *>(e->s_misc.p), blocks, iters, e->stream));
+    CU(fp64_probe_launch(static_cast<double *>(e->s_misc.p), blocks, iters, three_operands, e->stream));
     CU(cudaEventRecord(e->ev[2], e->stream));
     CU(cudaStreamSynchronize(e->stream));
     float ms = 0.f;
@@ -743,6 +743,8 @@ int tfhe_probe_fp64_tflops(tfhe_engine *e, double *tflops_out) {
   *tflops_out = best;
   return TFHE_OK;
 }
+int tfhe_probe_fp64_tflops(tfhe_engine *e, double *tflops_out) { return probe_fp64(e, false, tflops_out); }
+int tfhe_probe_fp64_3op_tflops(tfhe_engine *e, double *tflops_out) { return probe_fp64(e, true, tflops_out); }
 
 int tfhe_engine_load_cloud_key(tfhe_engine *e, uint32_t decomposition_offset,
                                const uint32_t *testvec_a, const uint32_t *testvec_b,

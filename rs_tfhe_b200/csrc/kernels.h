@@ -86,7 +86,7 @@ cudaError_t lut_generate_launch(const uint32_t *d_f_table, uint32_t modulus, dou
                                 uint32_t *d_tv_slot, cudaStream_t stream);
 cudaError_t extract_launch(const uint32_t *d_trlwe, uint32_t *d_ext, size_t count,
                            cudaStream_t stream);
-cudaError_t fp64_probe_launch(double *d_sink, int blocks, int iters, cudaStream_t stream);
+cudaError_t fp64_probe_launch(double *d_sink, int blocks, int iters, bool three_operands, cudaStream_t stream);
 
 // K6 (keygen.cu): cloud-key generation on the device
 cudaError_t keygen_launch(const cplx *tw_a, const cplx *tw_b, const uint32_t *d_s0,
