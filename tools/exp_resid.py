@@ -10,7 +10,7 @@ r = np.random.default_rng(1)
 eng = T.CudaBootstrap(P, 0)
 eng.generate_cloud_key(r.integers(0, 2, P.n, dtype=np.uint32), r.integers(0, 2, 1024, dtype=np.uint32), seed=7)
 res = {}
-for k in (1, 2, 3, 4, 8):
+for k in [int(x) for x in os.environ.get("RESID_K", "1,2,3,4,8").split(",")]:
     count = 148 * k
     pairs = r.integers(0, 2**32, (count, 2, P.n + 1), dtype=np.uint32)
     best = 1e9
