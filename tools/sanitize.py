@@ -17,8 +17,7 @@ for count in [5, int(os.environ.get("SANITIZE_TAIL", "160"))] + ([int(os.environ
     pairs = np.stack([K.encrypt_bool(a, rng), K.encrypt_bool(b, rng)], axis=1)
     ops = np.resize(np.array([0, 1, 2, 3, 5], dtype=np.uint8), count)
     out = e.batch_gate_mixed(ops, pairs)
-    ref = K.batch_gate(ops[:8], pairs[:8])
-    print(f"gates equal ({count}):", np.array_equal(out[:8], ref))
+    print(f"gates equal ({count}):", np.array_equal(out, K.batch_gate(ops, pairs)))
 lut_id, lut_b = e.lut_generate([1, 0], 2)
 ct = K.encrypt_message([1, 0], 2, rng)
 print("lut equal:", np.array_equal(e.batch_bootstrap_lut(lut_id, ct), K.batch_bootstrap(ct, lut_b=lut_b)))
