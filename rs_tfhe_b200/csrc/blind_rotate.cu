@@ -654,11 +654,11 @@ cudaError_t launch_t(const BrArgs &args, int num_sms, cudaStream_t stream) {
   if (args.count <= (size_t)br_latency_threshold(num_sms)) {
     // TFHE_BR_LATENCY_KERNEL=x selects the round-1 shape (l groups of 64 threads, gadgets with l > 1)
     static const bool old_shape = [] { const char *e = getenv("TFHE_BR_LATENCY_KERNEL"); return e && e[0] == 'x'; }();
-    // TFHE_BR_CLUSTER=1: up to one ciphertext per SM PAIR on a 2-CTA cluster (partial spectra through
-    // distributed shared memory).  Bit-exact but not the default: measured 2.10 ms per PBS against 2.00 ms
-    // for the one-CTA shape -- DSMEM moves ~20 B/clk and the cluster-scope fence flushes L1, which costs
-    // what halving the forward work saves (profiles/r2_experiments.json).
-    static const bool use_cluster = [] { const char *e = getenv("TFHE_BR_CLUSTER"); return e && e[0] == '1'; }();
+    // Up to one ciphertext per SM PAIR runs on a 2-CTA cluster: CTA c owns accumulator polynomial c, the partial
+    // spectra of the other output cross distributed shared memory as st.async writes that count their bytes on
+    // the peer's mbarrier (no cluster fence, no remote arrive: 1.48 ms per PBS at 128 bits against 2.00 ms on one
+    // SM; with a fence + remote arrive it was 2.10 -- profiles/r2_experiments.json).  TFHE_BR_CLUSTER=0 turns it off.
+    static const bool use_cluster = [] { const char *e = getenv("TFHE_BR_CLUSTER"); return !(e && e[0] == '0'); }();
     if (args.bsk3 && !old_shape && use_cluster && args.count <= (size_t)(num_sms / 2))
       return br_launch_cluster(L, BGBIT, args, num_sms, stream);
     if (args.bsk3 && !old_shape) return br_launch_latency_s(L, BGBIT, args, num_sms, stream);

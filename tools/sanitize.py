@@ -1,7 +1,7 @@
-"""Small workload for compute-sanitizer through the C ABI.  It reaches every shipped kernel shape: the latency
-kernel (5 gates), the 128-thread throughput kernel (a partial round), the 64-thread one (SANITIZE_COUNT > 592,
-optional: slow under the sanitizer), the 2-CTA cluster kernel (TFHE_BR_CLUSTER=1 in the environment), LUT
-bootstrap, extract + key switch, the FFT seam and a levelised circuit with a fused MUX."""
+"""Small workload for compute-sanitizer through the C ABI.  It reaches every shipped kernel shape: the 2-CTA
+cluster latency kernel (5 gates; TFHE_BR_CLUSTER=0 in the environment: the one-SM latency kernel instead), the
+128-thread throughput kernel (a partial round of 160 gates), the 64-thread one (SANITIZE_COUNT > 592),
+LUT bootstrap, extract + key switch, the FFT seam and a levelised circuit with a fused MUX."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
