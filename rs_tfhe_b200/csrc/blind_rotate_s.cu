@@ -586,11 +586,7 @@ blind_rotate_cluster_kernel(const BrArgs args) {
         const uint32_t abar = abar_s[i];
         // arm this step's receive barrier: the peer's reduced spectrum (4 x 128 complex) arrives as st.async writes
         if (ctid == 0) mbar_arrive_expect_tx(&xbar[par], (uint32_t)(kSlotCplx * 16));
-        cplx racc[2][4];
-#pragma unroll
-        for (int o = 0; o < 2; o++)
-#pragma unroll
-          for (int k = 0; k < 4; k++) racc[o][k] = mk(0.0, 0.0);
+        cplx rown[4];
         {
           uint32_t t_re[4], t_im[4];
           brs::load_t(T, acc, abar, args.offset, t_re, t_im);
@@ -608,42 +604,50 @@ blind_rotate_cluster_kernel(const BrArgs args) {
           brs::r4<false>(y, tcd[2], tcd[3]);
           mbar_wait(&full[g], parity);
           const cplx *rw = ring + g * brs::kRowCplx + T;
+          // The PEER's output first: its partial crosses distributed shared memory and is the longest leg of the
+          // step, so it is MACed, reduced over the l groups and on its way before this CTA's own output is touched.
+          cplx *mine = part + (size_t)par * (2 * L * kSlotCplx) + (size_t)g * kSlotCplx + T;
+          {
+            cplx rp[4];
+#pragma unroll
+            for (int kd = 0; kd < 4; kd++) {
+              rp[kd] = mk(0.0, 0.0);
+              cfma(rp[kd], y[kd], rw[(size_t)(kd * 2 + (int)peer) * brs::kT]);
+            }
+#pragma unroll
+            for (int kd = 0; kd < 4; kd++) mine[(size_t)L * kSlotCplx + kd * brs::kT] = rp[kd];   // peer's: slots l..2l-1
+          }
+          asm volatile("bar.sync 9, %0;" ::"n"(kCons) : "memory");   // every group's partial of the peer's output is in place
+          {
+            // all l x 128 threads share the reduce-and-ship: bin b of the 512; the group that runs the inverse
+            // afterwards (group 0) gets the fewest
+            const cplx *src = part + (size_t)par * (2 * L * kSlotCplx) + (size_t)L * kSlotCplx;
+            const uint32_t dst = part_remote + (uint32_t)((2 * (size_t)2 * L * kSlotCplx + (size_t)par * kSlotCplx) * 16);
+            for (int bin = (ctid + kCons - brs::kT) % kCons; bin < kSlotCplx; bin += kCons) {
+              cplx v = src[bin];
+#pragma unroll
+              for (int sl = 1; sl < L; sl++) v = cadd(v, src[(size_t)sl * kSlotCplx + bin]);
+              st_async_remote(dst + (uint32_t)(bin * 16), v, xbar_remote + 8u * par);
+            }
+          }
 #pragma unroll
           for (int kd = 0; kd < 4; kd++) {
-            cfma(racc[0][kd], y[kd], rw[(kd * 2 + 0) * brs::kT]);
-            cfma(racc[1][kd], y[kd], rw[(kd * 2 + 1) * brs::kT]);
+            rown[kd] = mk(0.0, 0.0);
+            cfma(rown[kd], y[kd], rw[(size_t)(kd * 2 + (int)rank) * brs::kT]);
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&empty[g]);
-        }
-        // Both outputs' partials go to local slots [o][g]; then the LAST group sums the peer's output over
-        // the l groups and ships ONE 8 KB spectrum through distributed shared memory (DSMEM moves only
-        // ~20 B/clk, so the l partials are reduced before they cross), while group 0 sums our own output.
-        {
-          cplx *mine = part + (size_t)par * (2 * L * kSlotCplx) + (size_t)g * kSlotCplx + T;
+          if (g != 0) {
 #pragma unroll
-          for (int kd = 0; kd < 4; kd++) {
-            mine[kd * brs::kT] = rank ? racc[1][kd] : racc[0][kd];                                  // ours: slots 0..l-1
-            mine[(size_t)L * kSlotCplx + kd * brs::kT] = rank ? racc[0][kd] : racc[1][kd];        // peer's: slots l..2l-1
+            for (int kd = 0; kd < 4; kd++) mine[kd * brs::kT] = rown[kd];                           // ours: slots 1..l-1
           }
         }
-        cta_sync();   // local partials visible; forward exchange buffers free
-        if (g == NG - 1) {
-          const cplx *src = part + (size_t)par * (2 * L * kSlotCplx) + (size_t)L * kSlotCplx + T;
-          const uint32_t dst = part_remote + (uint32_t)((2 * (size_t)2 * L * kSlotCplx + (size_t)par * kSlotCplx + T) * 16);
-#pragma unroll
-          for (int kd = 0; kd < 4; kd++) {
-            cplx v = src[kd * brs::kT];
-#pragma unroll
-            for (int sl = 1; sl < L; sl++) v = cadd(v, src[(size_t)sl * kSlotCplx + kd * brs::kT]);
-            st_async_remote(dst + (uint32_t)(kd * brs::kT * 16), v, xbar_remote + 8u * par);
-          }
-        }
+        cta_sync();   // our own output's partials visible; forward exchange buffers free
         if (g == 0) {
           cplx s[4];
           const cplx *src = part + (size_t)par * (2 * L * kSlotCplx) + T;
 #pragma unroll
-          for (int kd = 0; kd < 4; kd++) s[kd] = src[kd * brs::kT];
+          for (int kd = 0; kd < 4; kd++) s[kd] = rown[kd];
 #pragma unroll
           for (int sl = 1; sl < L; sl++)
 #pragma unroll
