@@ -24,12 +24,16 @@ for nd in sorted({1, n_dev}):
     e.load_cloud_key(ck)
     e.load_cloud_key(ck)                                   # second load: communicator already warm
     out = e.batch_gate_mixed(ops[:16384 * nd], pairs[:16384 * nd])   # warm-up (device + pinned staging allocations)
-    t = time.perf_counter()
-    out = e.batch_gate_mixed(ops, pairs)
-    dt = time.perf_counter() - t
+    dts = []
+    for rep in range(2):                                   # the first call also faults in the fresh output array
+        t = time.perf_counter()
+        out = e.batch_gate_mixed(ops, pairs)
+        dts.append(time.perf_counter() - t)
+    dt = min(dts)
     crc = int(out[:, -1].astype(np.uint64).sum() & 0xFFFFFFFF)
     res[f"gpus_{nd}"] = {"seconds": dt, "gates_per_s": total / dt, "key_broadcast_ms_warm": e.last_broadcast_ms(),
-                         "result_checksum": crc, "kernel_ms_slowest_device": e.last_kernel_ms()}
+                         "result_checksum": crc, "kernel_ms_slowest_device": e.last_kernel_ms(),
+                         "seconds_first_and_second_call": dts}
     base = base or dt
     res[f"gpus_{nd}"]["speedup_vs_1"] = base / dt
     e.close()
