@@ -234,7 +234,16 @@ int lut_count(const tfhe_engine *e) {
 // K4 dispatch: tensor-core GEMM for the gate sets, row-walk kernels otherwise
 int key_switch(tfhe_engine *e, const uint32_t *d_ext, uint32_t *d_out, size_t count) {
   const int variant = ks_variant();
-  if (variant == KS_UMMA && e->kumma) {
+  // latency path: up to 48 ciphertexts (a dependent chain's level; measured crossover with the tensor-core kernel ~70)
+  // split each ciphertext's sum over the whole GPU (TFHE_KS_SMALL_MAX overrides)
+  static const size_t small_max = [] { const char *v = getenv("TFHE_KS_SMALL_MAX"); return v ? (size_t)atoi(v) : (size_t)48; }();
+  if (count <= small_max && variant == KS_UMMA) {
+    KsArgs k{};
+    k.ksk = e->ksk(); k.ext = d_ext; k.out = d_out;
+    k.n = e->p.n; k.basebit = e->p.basebit; k.iks_t = e->p.iks_t;
+    k.stride = e->ksk_stride; k.zero_row = e->ksk_rows; k.n_in = TFHE_N; k.count = count;
+    CU(ks_small_launch(k, e->num_sms, e->stream));
+  } else if (variant == KS_UMMA && e->kumma) {
     KsUmmaArgs k{};
     k.key = e->kumma; k.ext = d_ext; k.out = d_out;
     k.n = e->p.n; k.iks_t = e->p.iks_t; k.basebit = e->p.basebit; k.count = count;

@@ -59,6 +59,8 @@ struct KsArgs {
   size_t count;
 };
 cudaError_t ks_launch(const KsArgs &args, cudaStream_t stream);
+// a handful of ciphertexts: the (i, j) terms of each split over ~2 CTAs per SM, partial sums combined with atomics
+cudaError_t ks_small_launch(const KsArgs &args, int num_sms, cudaStream_t stream);
 static inline uint32_t ks_stride(uint32_t n) { return (n + 1 + 3) & ~3u; }
 
 // K4 on the tcgen05 tensor cores (keyswitch_umma.cu): basebit 2..6 (gate sets, UINT1-6)

@@ -143,6 +143,58 @@ __global__ void __launch_bounds__(192) keyswitch_base4_kernel(const KsArgs a) {
   }
 }
 
+// ---- latency variant: a handful of ciphertexts (dependent PBS chains) -----------------------------------
+// The tensor-core key switch streams the whole 103 MB key whatever the batch size (0.2 ms); one ciphertext
+// needs 6912 of its rows (19 MB).  Here the N*t (i, j) terms of one ciphertext are split over `parts` CTAs:
+// each CTA adds up the rows its terms select (128-bit loads, eight rows in flight per thread) and subtracts its
+// partial sum from the output with atomics -- wrapping u32 arithmetic, so any order is bit-exact.  The output
+// must be zero on entry (the launcher clears it); part 0 adds res.b = src.b (trgsw.rs:343).
+__global__ void __launch_bounds__(320) keyswitch_small_kernel(const KsArgs a, uint32_t parts) {
+  extern __shared__ uint32_t s_row[];                 // selected row per term of this CTA (zero_row: digit 0)
+  const uint32_t N = a.n_in, t = a.iks_t;
+  const size_t ct = blockIdx.y;
+  const uint32_t terms = N * t;
+  const uint32_t t0 = (uint32_t)((uint64_t)terms * blockIdx.x / parts), t1 = (uint32_t)((uint64_t)terms * (blockIdx.x + 1) / parts);
+  const uint32_t prec = 1u << (32 - (1 + a.basebit * t));
+  const uint32_t mask = (1u << a.basebit) - 1u;
+  const uint32_t *src = a.ext + ct * (N + 1);
+  for (uint32_t x = t0 + threadIdx.x; x < t1; x += blockDim.x) {
+    const uint32_t i = x / t, j = x % t;
+    const uint32_t k = ((src[i] + prec) >> (32 - (j + 1) * a.basebit)) & mask;
+    s_row[x - t0] = k ? ((x << a.basebit) + k) : a.zero_row;
+  }
+  __syncthreads();
+  const uint32_t stride4 = a.stride >> 2;
+  const uint32_t x4 = threadIdx.x;
+  if (x4 >= stride4) return;
+  const uint4 *ksk4 = reinterpret_cast<const uint4 *>(a.ksk) + x4;
+  uint4 acc = make_uint4(0, 0, 0, 0);
+  const uint32_t cnt = t1 - t0;
+  uint32_t x = 0;
+  for (; x + 8 <= cnt; x += 8) {
+    uint4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) v[u] = __ldg(ksk4 + (size_t)s_row[x + u] * stride4);
+#pragma unroll
+    for (int u = 0; u < 8; u++) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+  }
+  for (; x < cnt; x++) {
+    const uint4 v = __ldg(ksk4 + (size_t)s_row[x] * stride4);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  uint32_t *o = a.out + ct * (a.n + 1);
+  const uint32_t vals[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    const uint32_t w = 4 * x4 + c;
+    if (w <= a.n) {
+      uint32_t d = 0u - vals[c];
+      if (blockIdx.x == 0 && w == a.n) d += src[N];
+      if (d) atomicAdd(o + w, d);
+    }
+  }
+}
+
 template <int T> cudaError_t launch_base4(const KsArgs &args, cudaStream_t stream) {
   const int smem = KS4_B * br::kN * 4;
   {  // per device and cheap: set on every launch (engines may live on several GPUs)
@@ -158,6 +210,22 @@ template <int T> cudaError_t launch_base4(const KsArgs &args, cudaStream_t strea
 }
 
 }  // namespace
+
+cudaError_t ks_small_launch(const KsArgs &args, int num_sms, cudaStream_t stream) {
+  if (args.count == 0) return cudaSuccess;
+  const uint32_t stride4 = args.stride >> 2;
+  const int threads = (int)((stride4 + 31) & ~31u);       // one thread per 4 output words, as in the row-walk kernels
+  if (threads > 320) return cudaErrorInvalidValue;
+  uint32_t parts = (uint32_t)((size_t)num_sms * 2 / args.count);
+  const uint32_t terms = args.n_in * args.iks_t;
+  if (parts < 1) parts = 1;
+  if (parts > terms / 8) parts = terms / 8;
+  const uint32_t per = (terms + parts - 1) / parts + 1;
+  cudaError_t e = cudaMemsetAsync(args.out, 0, args.count * (size_t)(args.n + 1) * 4, stream);
+  if (e != cudaSuccess) return e;
+  keyswitch_small_kernel<<<dim3(parts, (unsigned)args.count), threads, per * 4, stream>>>(args, parts);
+  return cudaGetLastError();
+}
 
 cudaError_t ks_launch(const KsArgs &args, cudaStream_t stream) {
   if (args.count == 0) return cudaSuccess;

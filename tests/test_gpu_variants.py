@@ -2,7 +2,8 @@
 64 threads per ciphertext with a 128-thread partial last round -- the default; 9: 128 threads per ciphertext
 on every round), the latency kernels forced on (TFHE_BR_LATENCY_MAX) and off, the 2-CTA cluster kernel (default for up
 to one ciphertext per SM pair) switched off (TFHE_BR_CLUSTER=0: the one-SM latency kernel), and the
-key-switch kernels (TFHE_KS_VARIANT=umma -- tcgen05, the default --, rows, TFHE_KS_GENERIC=1) run
+key-switch kernels (TFHE_KS_VARIANT=umma -- tcgen05, the default --, rows, TFHE_KS_GENERIC=1; the split-sum
+latency kernel for small batches forced off and on with TFHE_KS_SMALL_MAX) run
 tools/sanitize.py -- mixed gates at 5 / 160 (/ SANITIZE_COUNT) ciphertexts, LUT bootstrap, blind rotate +
 extract/key switch, each compared word for word with the oracle, plus the FFT seam and a small circuit -- in
 their own process (the selectors are read once per process)."""
@@ -21,7 +22,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     {"TFHE_BR_VARIANT": "9", "TFHE_BR_LATENCY_MAX": "0", "SANITIZE_COUNT": "601"},
     {"TFHE_BR_VARIANT": "9"}, {"TFHE_BR_LATENCY_MAX": "1000"}, {"TFHE_BR_CLUSTER": "0"},
     {"TFHE_BR_LATENCY_KERNEL": "x"},
-    {"TFHE_KS_VARIANT": "umma"}, {"TFHE_KS_VARIANT": "rows"}, {"TFHE_KS_VARIANT": "rows", "TFHE_KS_GENERIC": "1"},
+    {"TFHE_KS_VARIANT": "umma"}, {"TFHE_KS_VARIANT": "umma", "TFHE_KS_SMALL_MAX": "0"}, {"TFHE_KS_SMALL_MAX": "1000"},
+    {"TFHE_KS_VARIANT": "rows"}, {"TFHE_KS_VARIANT": "rows", "TFHE_KS_GENERIC": "1"},
 ], ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
 def test_variant_bit_exact(env):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sanitize.py")],
