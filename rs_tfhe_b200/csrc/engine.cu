@@ -237,7 +237,10 @@ int key_switch(tfhe_engine *e, const uint32_t *d_ext, uint32_t *d_out, size_t co
   // latency path: up to 48 ciphertexts (a dependent chain's level; measured crossover with the tensor-core kernel ~70)
   // split each ciphertext's sum over the whole GPU (TFHE_KS_SMALL_MAX overrides)
   static const size_t small_max = [] { const char *v = getenv("TFHE_KS_SMALL_MAX"); return v ? (size_t)atoi(v) : (size_t)48; }();
-  if (count <= small_max && variant == KS_UMMA) {
+  // (parameter sets the tensor-core kernel does not cover -- basebit 7 -- would fall to the row walk, whose
+  // latency is milliseconds at any batch size: for them the split-sum kernel stays ahead up to ~2000 ciphertexts)
+  const bool no_umma = variant == KS_UMMA && !e->kumma;
+  if ((count <= small_max || (no_umma && small_max > 0 && count <= 2048)) && variant == KS_UMMA) {
     KsArgs k{};
     k.ksk = e->ksk(); k.ext = d_ext; k.out = d_out;
     k.n = e->p.n; k.basebit = e->p.basebit; k.iks_t = e->p.iks_t;
