@@ -148,17 +148,18 @@ class Circuit:
         return sum(2 if self.gates[w].op == "MUX" else 1 for l in self.levels() for w in l)
 
 
-def evaluate(circuit: Circuit, engine: CudaBootstrap, inputs: np.ndarray) -> np.ndarray:
-    """Evaluate `circuit` on `inputs` u32[num_inputs][batch][n+1] (one ciphertext per input wire
-    and batch element).  Returns u32[num_outputs][batch][n+1].  The circuit is handed to the library
-    (tfhe_circuit_*), which levelises it and runs every level as one device batch with the wires
-    resident in HBM; `engine.last_kernel_ms()` afterwards holds the summed kernel times."""
+def _handle_for(circuit: Circuit, engine: CudaBootstrap):
+    """The library-side circuit of `circuit` on `engine`: recorded once and kept on the Circuit object, so
+    repeated evaluations reuse the compiled schedule that already sits on the device.  Recording more gates
+    or outputs, or switching engines, records afresh."""
     L = _load()
-    n1 = engine.params.n + 1
-    inputs = np.ascontiguousarray(inputs, dtype=np.uint32)
-    if inputs.ndim != 3 or inputs.shape[0] != len(circuit.inputs) or inputs.shape[2] != n1:
-        raise ValueError("inputs must be [num_inputs][batch][n+1]")
-    batch = inputs.shape[1]
+    key = (id(engine), engine._h.value, len(circuit.gates), tuple(circuit.outputs))
+    cached = getattr(circuit, "_native", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    if cached is not None:
+        L.tfhe_circuit_destroy(cached[1])
+        circuit._native = None
     h = C.c_void_p()
     _check(L.tfhe_circuit_create(engine._h, C.byref(h)))
     try:
@@ -181,11 +182,36 @@ def evaluate(circuit: Circuit, engine: CudaBootstrap, inputs: np.ndarray) -> np.
             wire[wid] = out.value
         for w in circuit.outputs:
             _check(L.tfhe_circuit_output(h, wire[w]))
-        res = np.empty((len(circuit.outputs), batch, n1), dtype=np.uint32)
-        _check(L.tfhe_circuit_run(h, inputs.ctypes.data_as(C.c_void_p), res.ctypes.data_as(C.c_void_p), batch))
-        lv, pbs, ks = C.c_uint32(), C.c_uint32(), C.c_uint32()
-        _check(L.tfhe_circuit_stats(h, C.byref(lv), C.byref(pbs), C.byref(ks)))
-        circuit.last_stats = {"levels": lv.value, "bootstraps": pbs.value, "key_switches": ks.value}
-        return res
-    finally:
+    except Exception:
         L.tfhe_circuit_destroy(h)
+        raise
+    circuit._native = (key, h, engine)      # the engine reference keeps it alive as long as the handle
+    return h
+
+
+def release(circuit: Circuit) -> None:
+    """Free the library-side circuit (before closing its engine)."""
+    cached = getattr(circuit, "_native", None)
+    if cached is not None:
+        _load().tfhe_circuit_destroy(cached[1])
+        circuit._native = None
+
+
+def evaluate(circuit: Circuit, engine: CudaBootstrap, inputs: np.ndarray) -> np.ndarray:
+    """Evaluate `circuit` on `inputs` u32[num_inputs][batch][n+1] (one ciphertext per input wire
+    and batch element).  Returns u32[num_outputs][batch][n+1].  The circuit is handed to the library
+    (tfhe_circuit_*), which levelises it and runs every level as one device batch with the wires
+    resident in HBM; `engine.last_kernel_ms()` afterwards holds the summed kernel times."""
+    L = _load()
+    n1 = engine.params.n + 1
+    inputs = np.ascontiguousarray(inputs, dtype=np.uint32)
+    if inputs.ndim != 3 or inputs.shape[0] != len(circuit.inputs) or inputs.shape[2] != n1:
+        raise ValueError("inputs must be [num_inputs][batch][n+1]")
+    batch = inputs.shape[1]
+    h = _handle_for(circuit, engine)
+    res = np.empty((len(circuit.outputs), batch, n1), dtype=np.uint32)
+    _check(L.tfhe_circuit_run(h, inputs.ctypes.data_as(C.c_void_p), res.ctypes.data_as(C.c_void_p), batch))
+    lv, pbs, ks = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    _check(L.tfhe_circuit_stats(h, C.byref(lv), C.byref(pbs), C.byref(ks)))
+    circuit.last_stats = {"levels": lv.value, "bootstraps": pbs.value, "key_switches": ks.value}
+    return res

@@ -73,6 +73,7 @@ struct CirNode {
 
 struct tfhe_circuit {
   tfhe_engine *e = nullptr;
+  int dev = 0;              // the engine's device: destroy must not touch an engine that may be gone already
   std::vector<CirNode> nodes;
   std::vector<uint32_t> inputs, outputs;
   // compiled form
@@ -82,6 +83,12 @@ struct tfhe_circuit {
   std::vector<Level> levels;
   std::vector<CirSrc> out_src;
   Scratch d_wires, d_pairs, d_ext, d_src, d_ops, d_out;
+  // device-resident schedule: every level's operand list (then the outputs') in d_src, uploaded once per compile;
+  // the per-row gate codes in d_ops, rebuilt only when the batch size changes
+  std::vector<size_t> src_off, ops_off;     // per level (+ one entry for the outputs in src_off)
+  bool src_on_device = false;
+  size_t ops_batch = 0;
+  std::vector<cudaEvent_t> ev;              // 4 per level: blind rotation start / end, key switch start / end
 };
 
 namespace {
@@ -146,6 +153,8 @@ int cir_compile(tfhe_circuit *c) {
   c->n_phys = phys;
   c->n_levels = maxd;
   c->compiled = true;
+  c->src_on_device = false;
+  c->ops_batch = 0;
   return TFHE_OK;
 }
 
@@ -171,14 +180,16 @@ int tfhe_circuit_create(tfhe_engine *e, tfhe_circuit **out) {
   tfhe_circuit *c = new (std::nothrow) tfhe_circuit();
   if (!c) return fail(TFHE_ERR_ALLOC, "out of host memory");
   c->e = e;
+  c->dev = e->dev;
   *out = c;
   return TFHE_OK;
 }
 
 void tfhe_circuit_destroy(tfhe_circuit *c) {
   if (!c) return;
-  cudaSetDevice(c->e->dev);
+  cudaSetDevice(c->dev);
   for (Scratch *s : {&c->d_wires, &c->d_pairs, &c->d_ext, &c->d_src, &c->d_ops, &c->d_out}) s->release();
+  for (cudaEvent_t ev : c->ev) cudaEventDestroy(ev);
   delete c;
 }
 
@@ -236,39 +247,64 @@ int tfhe_circuit_run(tfhe_circuit *c, const uint32_t *inputs, uint32_t *outputs,
   CU(cudaMemcpyAsync(wires, inputs, c->inputs.size() * batch * w * 4, cudaMemcpyHostToDevice, e->stream));
   float br_ms = 0.f, ks_ms = 0.f;
   tfhe_engine::Slot &sl = e->slot[0];
-  auto upload_src = [&](const std::vector<CirSrc> &src) -> int {
-    CU(c->d_src.reserve(src.size() * sizeof(CirSrc)));
-    CU(cudaMemcpyAsync(c->d_src.p, src.data(), src.size() * sizeof(CirSrc), cudaMemcpyHostToDevice, e->stream));
-    return TFHE_OK;
-  };
-  for (const tfhe_circuit::Level &lv : c->levels) {
+  // the schedule goes to the device once: operand lists at the first run after a compile, gate codes per batch size;
+  // a run then queues gather / blind rotation / combine / key switch level after level WITHOUT touching the host
+  // in between (kernel times come from per-level events read after the last level)
+  if (!c->src_on_device) {
+    std::vector<CirSrc> all;
+    c->src_off.clear();
+    for (const tfhe_circuit::Level &lv : c->levels) { c->src_off.push_back(all.size()); all.insert(all.end(), lv.src.begin(), lv.src.end()); }
+    c->src_off.push_back(all.size());
+    all.insert(all.end(), c->out_src.begin(), c->out_src.end());
+    CU(c->d_src.reserve(std::max<size_t>(all.size(), 1) * sizeof(CirSrc)));
+    CU(cudaMemcpyAsync(c->d_src.p, all.data(), all.size() * sizeof(CirSrc), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));   // `all` goes out of scope
+    c->src_on_device = true;
+  }
+  if (c->ops_batch != batch) {
+    std::vector<uint8_t> ops;
+    c->ops_off.clear();
+    for (const tfhe_circuit::Level &lv : c->levels) {
+      const size_t entries = lv.gates + 2 * (size_t)lv.muxes;
+      if (entries * batch > (size_t)1 << 22) return fail(TFHE_ERR_INVALID, "level too wide (%zu bootstraps); split the batch", entries * batch);
+      c->ops_off.push_back(ops.size());
+      for (size_t en = 0; en < entries; en++) ops.insert(ops.end(), batch, lv.ops[en]);
+    }
+    CU(c->d_ops.reserve(std::max<size_t>(ops.size(), 1)));
+    CU(cudaMemcpyAsync(c->d_ops.p, ops.data(), ops.size(), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    c->ops_batch = batch;
+  }
+  while (c->ev.size() < 4 * c->levels.size()) {
+    cudaEvent_t ev;
+    CU(cudaEventCreate(&ev));
+    c->ev.push_back(ev);
+  }
+  {   // size the level buffers once: a reallocation between levels would synchronise the device
+    size_t max_rows = 0;
+    for (const tfhe_circuit::Level &lv : c->levels) max_rows = std::max(max_rows, (lv.gates + 2 * (size_t)lv.muxes) * batch);
+    CU(c->d_pairs.reserve(std::max<size_t>(max_rows, 1) * 2 * w * 4));
+    CU(c->d_ext.reserve(std::max<size_t>(max_rows, 1) * W1 * 4));
+    CU(c->d_out.reserve(std::max<size_t>(c->out_src.size() * batch, 1) * w * 4));
+  }
+  const CirSrc *d_src = static_cast<const CirSrc *>(c->d_src.p);
+  for (size_t li = 0; li < c->levels.size(); li++) {
+    const tfhe_circuit::Level &lv = c->levels[li];
     const size_t entries = lv.gates + 2 * (size_t)lv.muxes, rows = entries * batch;
     const size_t ks_rows = (lv.gates + (size_t)lv.muxes) * batch;
-    if (rows > (size_t)1 << 22) return fail(TFHE_ERR_INVALID, "level too wide (%zu bootstraps); split the batch", rows);
-    rc = upload_src(lv.src);
-    if (rc != TFHE_OK) return rc;
-    std::vector<uint8_t> ops(rows);
-    for (size_t en = 0; en < entries; en++) memset(ops.data() + en * batch, lv.ops[en], batch);
-    CU(c->d_ops.reserve(rows));
-    CU(cudaMemcpyAsync(c->d_ops.p, ops.data(), rows, cudaMemcpyHostToDevice, e->stream));
-    CU(c->d_pairs.reserve(rows * 2 * w * 4));
-    CU(c->d_ext.reserve(rows * W1 * 4));
     circuit_gather_kernel<<<(unsigned)(rows * 2), 128, 0, e->stream>>>(
-        wires, static_cast<const CirSrc *>(c->d_src.p), static_cast<uint32_t *>(c->d_pairs.p), 2, batch, w);
+        wires, d_src + c->src_off[li], static_cast<uint32_t *>(c->d_pairs.p), 2, batch, w);
     CU(cudaGetLastError());
     e->launches++;
-    CU(cudaStreamSynchronize(e->stream));   // `ops` / lv.src host buffers may go out of scope
     uint32_t *ext = static_cast<uint32_t *>(c->d_ext.p);
+    CU(cudaEventRecord(c->ev[4 * li + 0], e->stream));
     for (size_t base = 0; base < rows; base += kChunk) {   // blind rotation, extracted at level 1
       const size_t n = rows - base < kChunk ? rows - base : kChunk;
-      rc = run_device(e, sl, 0, static_cast<const uint8_t *>(c->d_ops.p) + base,
+      rc = run_device(e, sl, 0, static_cast<const uint8_t *>(c->d_ops.p) + c->ops_off[li] + base,
                       -1, static_cast<const uint32_t *>(c->d_pairs.p) + base * 2 * w, ext + base * W1, n, 3);
       if (rc != TFHE_OK) return rc;
-      CU(cudaEventSynchronize(sl.ks_end));
-      float t = 0.f;
-      CU(cudaEventElapsedTime(&t, sl.br_start, sl.br_end));
-      br_ms += t;
     }
+    CU(cudaEventRecord(c->ev[4 * li + 1], e->stream));
     if (lv.muxes) {
       const size_t mrows = (size_t)lv.muxes * batch;
       uint32_t *u1 = ext + (size_t)lv.gates * batch * W1;
@@ -277,30 +313,31 @@ int tfhe_circuit_run(tfhe_circuit *c, const uint32_t *inputs, uint32_t *outputs,
       CU(cudaGetLastError());
       e->launches++;
     }
-    CU(cudaEventRecord(e->ev[0], e->stream));
+    CU(cudaEventRecord(c->ev[4 * li + 2], e->stream));
     uint32_t *dst = wires + (size_t)lv.phys0 * batch * w;
     for (size_t base = 0; base < ks_rows; base += kChunk) {
       const size_t n = ks_rows - base < kChunk ? ks_rows - base : kChunk;
       rc = key_switch(e, ext + base * W1, dst + base * w, n);
       if (rc != TFHE_OK) return rc;
     }
-    CU(cudaEventRecord(e->ev[1], e->stream));
-    CU(cudaEventSynchronize(e->ev[1]));
-    float t = 0.f;
-    CU(cudaEventElapsedTime(&t, e->ev[0], e->ev[1]));
-    ks_ms += t;
+    CU(cudaEventRecord(c->ev[4 * li + 3], e->stream));
   }
   // outputs (a NOT / constant / input may be an output): gather into [n_out][batch][w], then D2H
   if (!c->out_src.empty()) {
-    rc = upload_src(c->out_src);
-    if (rc != TFHE_OK) return rc;
     const size_t rows = c->out_src.size() * batch;
-    CU(c->d_out.reserve(rows * w * 4));
     circuit_gather_kernel<<<(unsigned)rows, 128, 0, e->stream>>>(
-        wires, static_cast<const CirSrc *>(c->d_src.p), static_cast<uint32_t *>(c->d_out.p), 1, batch, w);
+        wires, d_src + c->src_off[c->levels.size()], static_cast<uint32_t *>(c->d_out.p), 1, batch, w);
     CU(cudaGetLastError());
     e->launches++;
     CU(cudaMemcpyAsync(outputs, c->d_out.p, rows * w * 4, cudaMemcpyDeviceToHost, e->stream));
+  }
+  CU(cudaStreamSynchronize(e->stream));
+  for (size_t li = 0; li < c->levels.size(); li++) {
+    float t = 0.f;
+    CU(cudaEventElapsedTime(&t, c->ev[4 * li + 0], c->ev[4 * li + 1]));
+    br_ms += t;
+    CU(cudaEventElapsedTime(&t, c->ev[4 * li + 2], c->ev[4 * li + 3]));
+    ks_ms += t;
   }
   CU(cudaStreamSynchronize(e->stream));
   e->last_ms[0] = br_ms; e->last_ms[1] = ks_ms;
