@@ -41,6 +41,7 @@ def test_library_is_sm100a_with_tma():
     assert "DFMA" in sass and "USETMAXREG" in sass
     assert "UTCIMMA" in sass     # tcgen05.mma kind::i8: the key switch
     assert "LDTM" in sass and "STTM" in sass   # tcgen05.ld / .st: transform exchanges + constants in tensor memory
+    assert "STAS" in sass and "UCGABAR" in sass   # st.async into the cluster peer's shared memory, cluster barrier
 
 
 def test_no_gpu_fails_loudly():
