@@ -153,9 +153,9 @@ def _handle_for(circuit: Circuit, engine: CudaBootstrap):
     repeated evaluations reuse the compiled schedule that already sits on the device.  Recording more gates
     or outputs, or switching engines, records afresh."""
     L = _load()
-    key = (id(engine), engine._h.value, len(circuit.gates), tuple(circuit.outputs))
+    key = (engine._h.value, len(circuit.gates), tuple(circuit.outputs))
     cached = getattr(circuit, "_native", None)
-    if cached is not None and cached[0] == key:
+    if cached is not None and cached[0] == key and cached[2] is engine:   # the very same live engine object
         return cached[1]
     if cached is not None:
         L.tfhe_circuit_destroy(cached[1])
